@@ -1,0 +1,225 @@
+/* mnrf.h -- C ABI of the B200-native MultiNeRF per-ray core (libmnrf_b200.so).
+ *
+ * The reference (google-research/multinerf) has NO native boundary: its operator API is
+ * the Python signature `Model.__call__` (internal/models.py:75-312) plus the free
+ * functions of internal/{stepfun,render,coord}.py, all lowered by XLA.  This header is
+ * the boundary a maintainer would bind instead (ctypes stub in INTEGRATION.md); each entry
+ * names the reference code it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (fp32 row-major, samples on the
+ *    last axis, unless a parameter says bf16); entries only write their declared outputs;
+ *  - entries enqueue work on `stream` and return immediately: no allocation, no host
+ *    synchronisation, no global mutable state (except the tensor-map encoder lookup);
+ *  - return 0 on success, non-zero on error; the message is in mnrf_last_error()
+ *    (thread-local).  Python-side config errors of the reference (ValueError at trace
+ *    time) stay Python-side; the ABI reports shape / alignment / launch failures;
+ *  - bf16 buffers are raw uint16 storage (`mnrf_bf16`).
+ */
+#ifndef MNRF_H_
+#define MNRF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t mnrf_bf16;
+typedef void* mnrf_stream;   /* cudaStream_t */
+
+#define MNRF_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------- */
+int mnrf_abi_version(void);
+const char* mnrf_last_error(void);
+/* 1 if the current device is sm_100 (B200) and the tcgen05/TMA path can run. */
+int mnrf_device_ok(void);
+int mnrf_num_sms(void);
+
+/* ---- hierarchical resampling ---------------------------------------------------------
+ * Replaces, for one level: stepfun.max_dilate_weights (stepfun.py:116-128) + the [1:-1]
+ * trim (models.py:170-171) + the annealed logits (models.py:183-185) + stepfun.
+ * sample_intervals (stepfun.py:214-263: softmax, integrate_weights, sorted_interp
+ * math.py:108-127, midpoints).  One warp owns one ray.
+ *   sdist_prev [B, P+1], w_prev [B, P]           previous step function
+ *   u_base     [S]      host-computed linspace grid of stepfun.py:194-206
+ *   jitter     raw U[0,1): NULL | [B] (single_jitter) | [B, S]
+ *   cw_in      optional [B, P'+1] CDF to use instead of the internally computed one
+ *              (P' = 3P-2 with dilation, else P) -- lets tests pin the integer search
+ *   sdist_out  [B, S+1]
+ *   idx_out    optional int32 [B, S]: interval index #{cw <= u} - 1 (bit-exact contract)
+ *   cw_out     optional [B, P'+1]; tdil_out/wdil_out optional [B, P'+1] / [B, P'] (trimmed)
+ */
+typedef struct {
+  int32_t num_rays, num_prev, num_samples;
+  int32_t use_dilation;
+  float dilation, domain_lo, domain_hi;
+  float anneal, resample_padding;
+  int32_t jitter_mode;      /* 0 none, 1 per ray, 2 per sample */
+  float max_jitter;
+} mnrf_sample_desc;
+
+int mnrf_sample_level(const mnrf_sample_desc* d, const float* sdist_prev, const float* w_prev,
+                      const float* u_base, const float* jitter, const float* cw_in,
+                      float* sdist_out, int32_t* idx_out, float* cw_out, float* tdil_out,
+                      float* wdil_out, mnrf_stream stream);
+
+/* ---- ray casting + integrated positional encoding ------------------------------------
+ * Replaces coord.construct_ray_warps s_to_t (coord.py:63-99), render.cast_rays
+ * (render.py:103-127, diag=False), coord.track_linearize(contract) (coord.py:21-60),
+ * coord.lift_and_diagonalize (:129-133) and coord.integrated_pos_enc (:107-126).
+ *   sdist [B, S+1]; origins/directions [B,3]; radii/near/far [B]; basis [K,3]
+ *   feat_bf16  [B*S, ld_feat] row stride in elements; columns [2KL, feat_cols) zero-filled
+ *   feat_f32   optional [B*S, 2KL] (fp32 copy for parity tests)
+ *   tdist_out  optional [B, S+1]
+ */
+enum { MNRF_RAYDIST_NONE = 0, MNRF_RAYDIST_RECIPROCAL, MNRF_RAYDIST_LOG, MNRF_RAYDIST_EXP,
+       MNRF_RAYDIST_SQRT, MNRF_RAYDIST_SQUARE, MNRF_RAYDIST_PIECEWISE };
+enum { MNRF_RAY_CONE = 0, MNRF_RAY_CYLINDER = 1 };
+
+typedef struct {
+  int32_t num_rays, num_samples;
+  int32_t raydist_fn, ray_shape, warp_contract, disable_integration;
+  int32_t basis_k, min_deg, max_deg;
+  int32_t ld_feat, feat_cols;
+} mnrf_encode_desc;
+
+int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const float* origins,
+                const float* directions, const float* radii, const float* near,
+                const float* far, const float* basis, mnrf_bf16* feat_bf16, float* feat_f32,
+                float* tdist_out, mnrf_stream stream);
+
+/* View-direction positional encoding, coord.pos_enc (coord.py:136-147) with
+ * append_identity, broadcast over the S samples of each ray (models.py:550-554) and
+ * written as bf16 into columns [col0, col0 + 3 + 6*deg) of a [B*S, ld] buffer; columns up
+ * to col_end are zero-filled. */
+int mnrf_viewdir_enc(int32_t num_rays, int32_t num_samples, int32_t deg, const float* viewdirs,
+                     mnrf_bf16* out, int32_t ld, int32_t col0, int32_t col_end,
+                     mnrf_stream stream);
+
+/* ---- dense layers on tcgen05 ------------------------------------------------------------
+ * One Dense layer of models.py:436-437,455-460 (y = act(x W + b)) and its two backward
+ * GEMMs, bf16 operands, fp32 accumulation in TMEM.
+ *   mode FWD  : out[M,N] bf16 = act(A[M,K] * Bt[N,K]^T + bias[N])           (A, Bt K-major)
+ *   mode DGRAD: out[M,N] bf16 = (A[M,K] * Bt[N,K]^T + rowv[M]*colv[N]) masked by mask[M,N]>0
+ *               (A = dY, Bt = W in [in,out] layout; mask = stored activation; all optional)
+ *   mode WGRAD: out[Mo,N] fp32 += A[R,Mo]^T * B[R,N]   (A = X, B = dY, both row-major with
+ *               the reduction index R on rows: "MN-major" operands), split over R, fp32 atomics
+ * All leading dimensions are in elements.  K (or R) must be a multiple of 64 (16 for R),
+ * M-tiles are 128 rows; N must be a multiple of 16.
+ */
+enum { MNRF_GEMM_FWD = 0, MNRF_GEMM_DGRAD = 1, MNRF_GEMM_WGRAD = 2 };
+enum { MNRF_ACT_NONE = 0, MNRF_ACT_RELU = 1 };
+
+typedef struct {
+  int32_t mode, act;
+  int64_t m;          /* rows of the output (FWD/DGRAD: samples; WGRAD: `in` features) */
+  int32_t n, k;       /* output columns; reduction length (WGRAD: number of samples R) */
+  int64_t lda, ldb, ldc, ldmask;
+  int32_t impl;       /* 0 = tcgen05 (product path); 1 = SIMT reference kernel (bring-up/tests) */
+} mnrf_gemm_desc;
+
+int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
+              const float* rowv, const float* colv, const mnrf_bf16* mask, void* out,
+              mnrf_stream stream);
+
+/* ---- small heads (N <= 4 outputs): density / rgb / predicted normals ---------------------
+ * raw[M, n_out] = X[M, K](bf16) * W[n_out, K](bf16) + b, fp32 accumulate; models.py:460,585.
+ * Backward: dX[M, K] (bf16, optionally relu-masked by X > 0; optional accumulate is not
+ * provided -- the trunk adds the density term through mnrf_gemm's rowv/colv),
+ * dW[n_out, K] += , db[n_out] += (fp32 atomics).
+ */
+int mnrf_head_fwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
+                  const mnrf_bf16* w, const float* b, float* raw, mnrf_stream stream);
+int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
+                  const mnrf_bf16* w, const float* draw, mnrf_bf16* dx, int64_t lddx,
+                  int32_t relu_mask, float* dw, float* db, mnrf_stream stream);
+
+/* Column sums of a bf16 matrix into fp32 (bias gradients): out[N] += sum_m x[m, :]. */
+int mnrf_colsum(int64_t m, int32_t n, const mnrf_bf16* x, int64_t ldx, float* out,
+                mnrf_stream stream);
+
+/* ---- compositing ------------------------------------------------------------------------
+ * Forward: density activation (models.py:506) + rgb activation/padding (models.py:584-602)
+ * + render.compute_alpha_weights (render.py:130-151) + render.volumetric_rendering
+ * (render.py:154-213).  One warp owns one ray.
+ *   raw_density [B,S]; raw_rgb [B,S,3] or NULL (PropMLP: disable_rgb -> rgb = 0)
+ *   density_noise optional [B,S] N(0,1) draws (models.py:462-464)
+ *   sdist [B,S+1]; directions [B,3]; near/far [B]; bg: scalar or NULL->bg_rgb [B,3]
+ *   outputs: weights [B,S]; rgb_out [B,3]; optional density_out [B,S], rgb_samples [B,S,3]
+ *   extras (compute_extras): acc [B], dist [B,4] = (mean, p5, median, p95) or NULL
+ */
+enum { MNRF_RGB_SIGMOID = 0, MNRF_RGB_SAFE_EXP = 1 };
+
+typedef struct {
+  int32_t num_rays, num_samples;
+  int32_t raydist_fn, opaque_background;
+  float density_bias, density_noise;
+  int32_t rgb_act;
+  float rgb_premult, rgb_bias, rgb_padding;
+  float bg_const;
+} mnrf_composite_desc;
+
+int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw_density,
+                       const float* raw_rgb, const float* density_noise, const float* sdist,
+                       const float* directions, const float* near, const float* far,
+                       const float* bg_rgb, float* weights, float* rgb_out, float* density_out,
+                       float* rgb_samples, float* acc, float* dist, mnrf_stream stream);
+
+/* Losses + compositing backward for one level (train_utils.py:72-159 + the adjoint of
+ * render.py:130-213).  Fuses: data loss (mse | charb | rawnerf) on this level's pixel,
+ * distortion loss (final level), interlevel loss (proposal levels, against the final
+ * level's (sdist, weights)), then the alpha-compositing adjoint, the density-activation
+ * and rgb-activation derivatives.
+ *   outputs: d_raw_density [B,S]; d_raw_rgb [B,S,3] or NULL; stats[8] += (fp32 atomics):
+ *     [0] data loss (already weighted by data_mult)  [1] mse  [2] distortion  [3] interlevel
+ */
+enum { MNRF_LOSS_MSE = 0, MNRF_LOSS_CHARB = 1, MNRF_LOSS_RAWNERF = 2 };
+
+typedef struct {
+  mnrf_composite_desc c;
+  int32_t loss_type;
+  float charb_padding;
+  float data_mult;          /* data_loss_mult (final) or data_coarse_loss_mult (proposal) */
+  float distortion_mult;    /* 0 on proposal levels */
+  float interlevel_mult;    /* 0 on the final level */
+  int32_t num_samples_fine; /* S of the final level (interlevel) */
+  int32_t lossmult_channels;/* 1 or 3 */
+} mnrf_loss_desc;
+
+int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_density, const float* raw_rgb,
+                       const float* density_noise, const float* sdist, const float* directions,
+                       const float* near, const float* far, const float* bg_rgb,
+                       const float* weights, const float* rgb_out, const float* target_rgb,
+                       const float* lossmult, const float* inv_denom /* device scalar */,
+                       const float* sdist_fine, const float* weights_fine,
+                       float* d_raw_density, float* d_raw_rgb, float* stats,
+                       mnrf_stream stream);
+
+/* ---- optimizer ---------------------------------------------------------------------------
+ * train_utils.clip_gradients (train_utils.py:200-218: value clip, then global-norm clip with
+ * eps in the denominator), nan_to_num (:328) and optax.adam on one flat fp32 parameter
+ * group (one top-level module).  norm_sq_scratch: device float[1], zeroed by the call.
+ */
+typedef struct {
+  int64_t n;
+  float grad_max_val, grad_max_norm;
+  float lr, beta1, beta2, eps;
+  int32_t step;             /* 1-based update count t */
+  float grad_scale;         /* multiplies the raw gradient first (1/world_size for pmean) */
+} mnrf_adam_desc;
+
+int mnrf_clip_adam(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
+                   float* nu, float* norm_sq_scratch, mnrf_stream stream);
+
+/* fp32 master [in_pad, out] (row-major) -> bf16 shadows: w_nk [out, in_pad] (K-major operand
+ * of the forward GEMM) and w_kn [in_pad, out] (K-major operand of the dgrad GEMM). */
+int mnrf_pack_weights(int32_t in_pad, int32_t out, const float* master, mnrf_bf16* w_nk,
+                      mnrf_bf16* w_kn, mnrf_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* MNRF_H_ */

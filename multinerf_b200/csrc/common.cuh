@@ -1,0 +1,123 @@
+// Internal helpers shared by the kernels of libmnrf_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mnrf.h"
+
+namespace mnrf {
+
+void set_error(const char* fmt, ...);
+
+#define MNRF_CHECK(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::mnrf::set_error(__VA_ARGS__);    \
+      return 1;                          \
+    }                                    \
+  } while (0)
+
+#define MNRF_CUDA(expr)                                                               \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::mnrf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                        __FILE__, __LINE__);                                          \
+      return 2;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+#define MNRF_LAUNCH_CHECK() MNRF_CUDA(cudaGetLastError())
+
+constexpr float kEps = 1.1920929e-07f;        // jnp.finfo(float32).eps
+constexpr float kEpsSq = 1.4210855e-14f;      // eps**2 (stepfun.py:89,121)
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+// Inclusive prefix sum across the 32 lanes.
+__device__ __forceinline__ float warp_scan_incl(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+// Inclusive suffix sum across the 32 lanes.
+__device__ __forceinline__ float warp_scan_incl_rev(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_down_sync(kFull, v, o);
+    if (lane + o < 32) v += n;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // jax.nn.softplus = logaddexp(x, 0) = max(x,0) + log1p(exp(-|x|))
+  return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// math.safe_sin (math.py:26-38): sin(|x| < 100*pi ? x : x mod 100*pi), Python-style mod.
+__device__ __forceinline__ float safe_sin_f(float x) {
+  const float t = 314.159271240234375f;  // fl32(100*pi)
+  if (!(fabsf(x) < t)) {
+    float r = fmodf(x, t);
+    if (r != 0.f && (r < 0.f)) r += t;
+    x = r;
+  }
+  return sinf(x);
+}
+
+// s_to_t of coord.construct_ray_warps (coord.py:63-99) for one value.
+__device__ __forceinline__ float fwd_raydist(int fn, float x) {
+  switch (fn) {
+    case MNRF_RAYDIST_RECIPROCAL: return 1.f / x;
+    case MNRF_RAYDIST_LOG: return logf(x);
+    case MNRF_RAYDIST_EXP: return expf(x);
+    case MNRF_RAYDIST_SQRT: return sqrtf(x);
+    case MNRF_RAYDIST_SQUARE: return x * x;
+    case MNRF_RAYDIST_PIECEWISE: return x < 1.f ? 0.5f * x : 1.f - 0.5f / x;
+    default: return x;
+  }
+}
+__device__ __forceinline__ float inv_raydist(int fn, float x) {
+  switch (fn) {
+    case MNRF_RAYDIST_RECIPROCAL: return 1.f / x;
+    case MNRF_RAYDIST_LOG: return expf(x);
+    case MNRF_RAYDIST_EXP: return logf(x);
+    case MNRF_RAYDIST_SQRT: return x * x;
+    case MNRF_RAYDIST_SQUARE: return sqrtf(x);
+    case MNRF_RAYDIST_PIECEWISE: return x < 0.5f ? 2.f * x : 0.5f / (1.f - x);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float s_to_t(int fn, float s, float s_near, float s_far) {
+  // fn_inv(s * s_far + (1 - s) * s_near), products and sum rounded separately like XLA's
+  // unfused elementwise graph.
+  return inv_raydist(fn, __fadd_rn(__fmul_rn(s, s_far), __fmul_rn(__fsub_rn(1.f, s), s_near)));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace mnrf

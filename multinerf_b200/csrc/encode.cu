@@ -1,0 +1,231 @@
+// Ray casting + integrated positional encoding: one warp owns one ray, loops over its samples.
+//
+// Replaces (reference file:line): coord.construct_ray_warps s_to_t coord.py:63-99;
+// render.cast_rays render.py:103-127 -> conical_frustum_to_gaussian :44-78 (stable form) /
+// cylinder_to_gaussian :81-100 -> lift_gaussian :21-41 (diag=False, models.py:213);
+// coord.contract + track_linearize coord.py:21-60 (closed-form Jacobian);
+// coord.lift_and_diagonalize :129-133; coord.integrated_pos_enc :107-126 with
+// math.safe_sin math.py:26-38.  Also coord.pos_enc :136-147 for the view directions.
+//
+// Output: bf16 feature rows written straight into the MLP's input buffer (row stride
+// ld_feat), staged through shared memory so that each lane stores 16 B.
+#include "common.cuh"
+
+namespace mnrf {
+
+struct Gauss {
+  float mean[3];
+  float cov[3][3];
+};
+
+__device__ __forceinline__ void cast_one(int ray_shape, float t0, float t1, const float o[3],
+                                         const float dvec[3], float radius, Gauss& g) {
+  float t_mean, t_var, r_var;
+  if (ray_shape == MNRF_RAY_CONE) {
+    float mu = (t0 + t1) / 2.f;
+    float hw = (t1 - t0) / 2.f;
+    float hw2 = hw * hw, mu2 = mu * mu;
+    float hw4 = hw2 * hw2;
+    float denom = fmaxf(kEps, 3.f * mu2 + hw2);
+    t_mean = mu + (2.f * mu * hw2) / denom;
+    t_var = hw2 / 3.f - (4.f / 15.f) * hw4 * (12.f * mu2 - hw2) / (denom * denom);
+    r_var = mu2 / 4.f + (5.f / 12.f) * hw2 - (4.f / 15.f) * hw4 / denom;
+    r_var = r_var * (radius * radius);
+  } else {
+    t_mean = (t0 + t1) / 2.f;
+    r_var = (radius * radius) / 4.f;
+    float dt = t1 - t0;
+    t_var = (dt * dt) / 12.f;
+  }
+  float dmag = fmaxf(1e-10f, dvec[0] * dvec[0] + dvec[1] * dvec[1] + dvec[2] * dvec[2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    g.mean[i] = dvec[i] * t_mean + o[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float d_outer = dvec[i] * dvec[j];
+      float null_outer = (i == j ? 1.f : 0.f) - dvec[i] * (dvec[j] / dmag);
+      g.cov[i][j] = t_var * d_outer + r_var * null_outer;
+    }
+  }
+}
+
+__device__ __forceinline__ void contract_gauss(Gauss& g) {
+  float x0 = g.mean[0], x1 = g.mean[1], x2 = g.mean[2];
+  float m = fmaxf(kEps, x0 * x0 + x1 * x1 + x2 * x2);
+  if (m <= 1.f) return;
+  float r = sqrtf(m);
+  float scale = (2.f * r - 1.f) / m;
+  float s = 2.f / r - 1.f / m;
+  float c = 2.f / (m * m) - 2.f / (m * r);
+  float x[3] = {x0, x1, x2};
+  float J[3][3], T[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) J[i][j] = (i == j ? s : 0.f) + c * x[i] * x[j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      T[i][j] = J[i][0] * g.cov[0][j] + J[i][1] * g.cov[1][j] + J[i][2] * g.cov[2][j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      g.cov[i][j] = T[i][0] * J[j][0] + T[i][1] * J[j][1] + T[i][2] * J[j][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) g.mean[i] = scale * x[i];
+}
+
+// smem per warp: tdist[S+1] floats | lift_mean[K] | lift_var[K] | basis[3K] (block-shared) |
+//                row[feat_cols] bf16
+__global__ void __launch_bounds__(256)
+encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
+              const float* __restrict__ origins, const float* __restrict__ directions,
+              const float* __restrict__ radii, const float* __restrict__ near,
+              const float* __restrict__ far, const float* __restrict__ basis,
+              __nv_bfloat16* __restrict__ feat, float* __restrict__ feat_f32,
+              float* __restrict__ tdist_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int S = d.num_samples, K = d.basis_k, L = d.max_deg - d.min_deg, KL = K * L;
+  float* sb = reinterpret_cast<float*>(smem_raw);                 // basis [K][3]
+  const int row_bytes = ((d.feat_cols * 2 + 15) / 16) * 16;
+  const int per_warp_f = (S + 1) + 2 * K;
+  float* wbase = sb + 3 * K + (size_t)wib * per_warp_f;
+  float* tds = wbase;
+  float* lm = tds + (S + 1);
+  float* lv = lm + K;
+  unsigned char* rows = smem_raw + (((size_t)(3 * K + nw * per_warp_f) * 4 + 15) / 16) * 16;
+  __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(rows + (size_t)wib * row_bytes);
+
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) sb[i] = basis[i];
+  __syncthreads();
+  for (int i = lane; i < d.feat_cols; i += 32) row[i] = __float2bfloat16(0.f);
+
+  for (int ray = blockIdx.x * nw + wib; ray < d.num_rays; ray += gridDim.x * nw) {
+    const float o[3] = {origins[ray * 3 + 0], origins[ray * 3 + 1], origins[ray * 3 + 2]};
+    const float dv[3] = {directions[ray * 3 + 0], directions[ray * 3 + 1], directions[ray * 3 + 2]};
+    const float radius = radii[ray];
+    const float s_near = fwd_raydist(d.raydist_fn, near[ray]);
+    const float s_far = fwd_raydist(d.raydist_fn, far[ray]);
+    for (int i = lane; i <= S; i += 32) {
+      float t = s_to_t(d.raydist_fn, sdist[(size_t)ray * (S + 1) + i], s_near, s_far);
+      tds[i] = t;
+      if (tdist_out) tdist_out[(size_t)ray * (S + 1) + i] = t;
+    }
+    __syncwarp();
+    for (int s = 0; s < S; ++s) {
+      Gauss g;
+      cast_one(d.ray_shape, tds[s], tds[s + 1], o, dv, radius, g);
+      if (d.warp_contract) contract_gauss(g);
+      for (int k = lane; k < K; k += 32) {
+        float b0 = sb[k * 3 + 0], b1 = sb[k * 3 + 1], b2 = sb[k * 3 + 2];
+        lm[k] = g.mean[0] * b0 + g.mean[1] * b1 + g.mean[2] * b2;
+        float c0 = g.cov[0][0] * b0 + g.cov[0][1] * b1 + g.cov[0][2] * b2;
+        float c1 = g.cov[1][0] * b0 + g.cov[1][1] * b1 + g.cov[1][2] * b2;
+        float c2 = g.cov[2][0] * b0 + g.cov[2][1] * b1 + g.cov[2][2] * b2;
+        lv[k] = d.disable_integration ? 0.f : (b0 * c0 + b1 * c1 + b2 * c2);
+      }
+      __syncwarp();
+      const size_t m = (size_t)ray * S + s;
+      for (int f = lane; f < KL; f += 32) {
+        int l = f / K, k = f - l * K;
+        float sc = exp2f((float)(d.min_deg + l));
+        float y = lm[k] * sc;
+        float v = lv[k] * (sc * sc);
+        float e = expf(-0.5f * v);
+        float fs = e * safe_sin_f(y);
+        float fc = e * safe_sin_f(y + 1.57079637050628662109375f);
+        row[f] = __float2bfloat16(fs);
+        row[KL + f] = __float2bfloat16(fc);
+        if (feat_f32) {
+          feat_f32[m * (2 * KL) + f] = fs;
+          feat_f32[m * (2 * KL) + KL + f] = fc;
+        }
+      }
+      __syncwarp();
+      const uint4* src = reinterpret_cast<const uint4*>(row);
+      uint4* dst = reinterpret_cast<uint4*>(feat + m * (size_t)d.ld_feat);
+      for (int c = lane; c < row_bytes / 16; c += 32) dst[c] = src[c];
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void viewdir_enc_kernel(int num_rays, int S, int deg, const float* __restrict__ viewdirs,
+                                   __nv_bfloat16* __restrict__ out, int ld, int col0, int col_end) {
+  // one thread per (row, column) of the [col0, col_end) slab; consecutive threads -> columns
+  const int width = col_end - col0;
+  const size_t total = (size_t)num_rays * S * width;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t rowi = i / width;
+    int c = (int)(i - rowi * width);
+    int ray = (int)(rowi / S);
+    float v = 0.f;
+    if (c < 3) {
+      v = viewdirs[ray * 3 + c];
+    } else if (c < 3 + 6 * deg) {
+      int f = c - 3;
+      int half = f / (3 * deg);
+      f -= half * 3 * deg;
+      int l = f / 3, ch = f - l * 3;
+      float x = viewdirs[ray * 3 + ch] * exp2f((float)l);
+      v = sinf(half ? x + 1.57079637050628662109375f : x);   // plain sin (coord.py:143-144)
+    }
+    out[rowi * (size_t)ld + col0 + c] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace mnrf
+
+extern "C" int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const float* origins,
+                           const float* directions, const float* radii, const float* near,
+                           const float* far, const float* basis, mnrf_bf16* feat_bf16,
+                           float* feat_f32, float* tdist_out, mnrf_stream stream) {
+  using namespace mnrf;
+  MNRF_CHECK(d && sdist && origins && directions && radii && near && far && basis && feat_bf16,
+             "mnrf_encode: null pointer");
+  MNRF_CHECK(d->ray_shape == MNRF_RAY_CONE || d->ray_shape == MNRF_RAY_CYLINDER,
+             "ray_shape must be 'cone' or 'cylinder'");
+  const int KL2 = 2 * d->basis_k * (d->max_deg - d->min_deg);
+  MNRF_CHECK(d->feat_cols >= KL2 && d->ld_feat >= d->feat_cols, "mnrf_encode: feat_cols %d < 2KL %d or ld %d",
+             d->feat_cols, KL2, d->ld_feat);
+  MNRF_CHECK(d->feat_cols % 8 == 0 && d->ld_feat % 8 == 0 && ((uintptr_t)feat_bf16 % 16) == 0,
+             "mnrf_encode: feature rows must be 16-byte aligned");
+  if (d->num_rays == 0) return 0;
+  int nw = 8;
+  const int row_bytes = ((d->feat_cols * 2 + 15) / 16) * 16;
+  size_t smem = (((size_t)(3 * d->basis_k + nw * ((d->num_samples + 1) + 2 * d->basis_k)) * 4 + 15) / 16) * 16 +
+                (size_t)nw * row_bytes;
+  MNRF_CHECK(smem <= 200 * 1024, "mnrf_encode: shared memory %zu too large", smem);
+  MNRF_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks = ceil_div(d->num_rays, nw);
+  const int max_blocks = mnrf_num_sms() * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  encode_kernel<<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
+      *d, sdist, origins, directions, radii, near, far, basis,
+      reinterpret_cast<__nv_bfloat16*>(feat_bf16), feat_f32, tdist_out);
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mnrf_viewdir_enc(int32_t num_rays, int32_t num_samples, int32_t deg,
+                                const float* viewdirs, mnrf_bf16* out, int32_t ld, int32_t col0,
+                                int32_t col_end, mnrf_stream stream) {
+  using namespace mnrf;
+  MNRF_CHECK(viewdirs && out, "mnrf_viewdir_enc: null pointer");
+  MNRF_CHECK(col_end - col0 >= 3 + 6 * deg && col_end <= ld, "mnrf_viewdir_enc: slab [%d,%d) too small for deg %d",
+             col0, col_end, deg);
+  if (num_rays == 0) return 0;
+  size_t total = (size_t)num_rays * num_samples * (col_end - col0);
+  int blocks = (int)((total + 255) / 256);
+  int maxb = mnrf_num_sms() * 16;
+  if (blocks > maxb) blocks = maxb;
+  viewdir_enc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      num_rays, num_samples, deg, viewdirs, reinterpret_cast<__nv_bfloat16*>(out), ld, col0, col_end);
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,477 @@
+// Dense layers of the PropMLP / NerfMLP on 5th-gen tensor cores (sm_100a): persistent,
+// warp-specialised GEMM with TMA-staged operands, tcgen05.mma accumulating in TMEM and a fused
+// epilogue.  Replaces nn.Dense (+ReLU, + skip-concat as a wider K) of models.py:436-437,455-460,
+// 527,577 and the dgrad / wgrad GEMMs jax.value_and_grad derives from them
+// (train_utils.py:316-317).
+//
+//   warp 0   : TMA producer (one elected lane) -- cp.async.bulk.tensor.2d into a 4-stage ring
+//   warp 1   : MMA issuer  (one elected lane) -- tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256
+//   warp 2   : TMEM allocator (512 columns = two 256-column accumulator stages)
+//   warps 4-7: epilogue -- tcgen05.ld 32x32b, bias/ReLU | mask/rank-1 | fp32 reduction, stores
+//
+// Operand layouts (all bf16, 128-byte swizzle):
+//   FWD / DGRAD : A[M,K] and B[N,K] are K-major (reduction index contiguous);
+//   WGRAD       : A = X[R,Mo] and B = dY[R,N] are "MN-major" (reduction index R on rows):
+//                 out[Mo,N] += X^T dY, split over R with fp32 vector reductions.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mnrf {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int MAX_BLOCK_N = 256;
+constexpr int NUM_STAGES = 4;
+constexpr int NUM_ACC = 2;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
+constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KiB
+constexpr int SMEM_BYTES = NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256;
+constexpr int NUM_THREADS = 256;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "selp.u32 %0, 1, 0, %%px;\n"
+      "}\n"
+      : "=r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (error surfaces on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mnrf gemm_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                      // c_format = F32
+         | (1u << 7)                    // a_format = BF16
+         | (1u << 10)                   // b_format = BF16
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmParams {
+  int mode, act;
+  int64_t m;                  // output rows
+  int n, k;                   // output cols, reduction length
+  int block_n;                // N tile (<= 256, multiple of 16, divides n)
+  int num_m_blocks, num_n_blocks, num_splits, kblocks_per_split, num_k_blocks;
+  int64_t ldc, ldmask;
+  const float* bias;
+  const float* rowv;
+  const float* colv;
+  const __nv_bfloat16* mask;
+  void* out;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + NUM_STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;                       // [NUM_STAGES]
+  uint64_t* empty_bar = bars + NUM_STAGES;         // [NUM_STAGES]
+  uint64_t* tfull_bar = bars + 2 * NUM_STAGES;     // [NUM_ACC]
+  uint64_t* tempty_bar = tfull_bar + NUM_ACC;      // [NUM_ACC]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + NUM_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
+  constexpr bool kWgrad = (MODE == MNRF_GEMM_WGRAD);
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < NUM_ACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.num_n_blocks;
+        const int rest = tile / p.num_n_blocks;
+        const int m_blk = rest % p.num_m_blocks;
+        const int split = rest / p.num_m_blocks;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+          if (!kWgrad) {
+            // K-major: box = [64 k][rows]
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n);
+          } else {
+            // MN-major: one box per 64-wide MN atom = [64 mn][64 r], atoms BLOCK_K*128 bytes apart
+            for (int a = 0; a < BLOCK_M / 64; ++a)
+              tma_load_2d(sa + a * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + a * 64, kb * BLOCK_K);
+            for (int a = 0; a < p.block_n / 64; ++a)
+              tma_load_2d(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_blk * p.block_n + a * 64, kb * BLOCK_K);
+          }
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(BLOCK_M, p.block_n, kWgrad ? 1 : 0, kWgrad ? 1 : 0);
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int rest = tile / p.num_n_blocks;
+      const int split = rest / p.num_m_blocks;
+      const int kb0 = split * p.kblocks_per_split;
+      const int kb1 = min(p.num_k_blocks, kb0 + p.kblocks_per_split);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * MAX_BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 3);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            uint64_t adesc, bdesc;
+            if (!kWgrad) {
+              // K-major, SW128: 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the span
+              adesc = make_smem_desc(sa + k * (UMMA_K * 2), 0, 1024);
+              bdesc = make_smem_desc(sb + k * (UMMA_K * 2), 0, 1024);
+            } else {
+              // MN-major, SW128: LBO = stride between 64-wide MN atoms, SBO = stride between
+              // 8-row k groups; advance 16 k rows = 2048 B per UMMA_K
+              adesc = make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
+              bdesc = make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
+            }
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile % p.num_n_blocks;
+      const int rest = tile / p.num_n_blocks;
+      const int m_blk = rest % p.num_m_blocks;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      const int64_t row = (int64_t)m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.m;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N;
+      float rv = 0.f;
+      if (MODE == MNRF_GEMM_DGRAD && p.rowv && row_ok) rv = p.rowv[row];
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + c0, r);
+        tmem_ld_wait();
+        const int col = n_blk * p.block_n + c0;
+        if (row_ok) {
+          if (MODE == MNRF_GEMM_WGRAD) {
+            float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (c0 + j < p.block_n)
+                red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+          } else {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (MODE == MNRF_GEMM_FWD) {
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + min(col + j, p.n - 1));
+              }
+              if (p.act == MNRF_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+            } else {
+              if (p.rowv) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += rv * __ldg(p.colv + min(col + j, p.n - 1));
+              }
+              if (p.mask) {
+                const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.ldmask + col);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  if (c0 + g * 8 < p.block_n) {
+                    uint4 mv = mp[g];
+                    uint32_t mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      if (!(bf16_lo(mm[e]) > 0.f)) v[g * 8 + 2 * e] = 0.f;
+                      if (!(bf16_hi(mm[e]) > 0.f)) v[g * 8 + 2 * e + 1] = 0.f;
+                    }
+                  }
+                }
+              }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (c0 + g * 8 < p.block_n) {
+                uint4 o;
+                o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                dst[g] = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] (cols contiguous, row pitch ld elements), box = [box_cols, box_rows].
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                     int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  MNRF_CHECK(fn, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MNRF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d base=%p",
+             (int)r, (long long)rows, (long long)cols, (long long)ld, box_cols, box_rows, base);
+  return 0;
+}
+
+static int pick_block_n(int n) {
+  const int cands[] = {256, 128, 64, 32, 16};
+  for (int c : cands)
+    if (n % c == 0) return c;
+  return 0;
+}
+
+int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
+                   const float* rowv, const float* colv, const mnrf_bf16* mask, void* out,
+                   cudaStream_t stream) {
+  MNRF_CHECK(d->k % BLOCK_K == 0, "mnrf_gemm(tc): reduction length %d must be a multiple of %d", d->k, BLOCK_K);
+  MNRF_CHECK(d->lda % 8 == 0 && d->ldb % 8 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0,
+             "mnrf_gemm(tc): operands must be 16-byte aligned with ld %% 8 == 0");
+  GemmParams p{};
+  p.mode = d->mode; p.act = d->act; p.m = d->m; p.n = d->n; p.k = d->k;
+  p.block_n = pick_block_n(d->n);
+  MNRF_CHECK(p.block_n > 0, "mnrf_gemm(tc): N=%d must be a multiple of 16", d->n);
+  if (d->mode == MNRF_GEMM_WGRAD)
+    MNRF_CHECK(p.block_n >= 64, "mnrf_gemm(tc): WGRAD needs N %% 64 == 0 (MN-major 128-byte atoms), N=%d", d->n);
+  p.num_m_blocks = (int)((d->m + BLOCK_M - 1) / BLOCK_M);
+  p.num_n_blocks = d->n / p.block_n;
+  p.num_k_blocks = d->k / BLOCK_K;
+  p.ldc = d->ldc; p.ldmask = d->ldmask;
+  p.bias = bias; p.rowv = rowv; p.colv = colv;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(mask);
+  p.out = out;
+  const int sms = mnrf_num_sms();
+  p.num_splits = 1;
+  if (d->mode == MNRF_GEMM_WGRAD) {
+    const int out_tiles = p.num_m_blocks * p.num_n_blocks;
+    int splits = std::max(1, (2 * sms) / out_tiles);
+    splits = std::min(splits, p.num_k_blocks);
+    p.num_splits = splits;
+  }
+  p.kblocks_per_split = (p.num_k_blocks + p.num_splits - 1) / p.num_splits;
+  p.num_splits = (p.num_k_blocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  if (d->mode != MNRF_GEMM_WGRAD) {
+    MNRF_CHECK(d->ldc % 8 == 0 && ((uintptr_t)out % 16) == 0, "mnrf_gemm(tc): bf16 output must be 16-byte aligned");
+    if (mask) MNRF_CHECK(d->ldmask % 8 == 0 && ((uintptr_t)mask % 16) == 0, "mnrf_gemm(tc): mask must be 16-byte aligned");
+  } else {
+    MNRF_CHECK(d->ldc % 4 == 0 && ((uintptr_t)out % 16) == 0, "mnrf_gemm(tc): fp32 output must be 16-byte aligned");
+  }
+
+  CUtensorMap ta, tb;
+  if (d->mode != MNRF_GEMM_WGRAD) {
+    if (make_tmap(&ta, a, d->m, d->k, d->lda, BLOCK_K, BLOCK_M)) return 1;
+    if (make_tmap(&tb, b, d->n, d->k, d->ldb, BLOCK_K, p.block_n)) return 1;
+  } else {
+    // A = X[R, Mo], B = dY[R, N]; reduction index on rows
+    if (make_tmap(&ta, a, d->k, d->m, d->lda, 64, BLOCK_K)) return 1;
+    if (make_tmap(&tb, b, d->k, d->n, d->ldb, 64, BLOCK_K)) return 1;
+  }
+  const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
+  const int grid = std::min(total_tiles, sms);
+  if (grid == 0) return 0;
+#define MNRF_LAUNCH_TC(MODE_)                                                                         \
+  do {                                                                                                \
+    static bool attr_set = false;                                                                     \
+    if (!attr_set) {                                                                                  \
+      MNRF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+      attr_set = true;                                                                                \
+    }                                                                                                 \
+    gemm_tc_kernel<MODE_><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);                      \
+  } while (0)
+  if (d->mode == MNRF_GEMM_FWD) MNRF_LAUNCH_TC(MNRF_GEMM_FWD);
+  else if (d->mode == MNRF_GEMM_DGRAD) MNRF_LAUNCH_TC(MNRF_GEMM_DGRAD);
+  else MNRF_LAUNCH_TC(MNRF_GEMM_WGRAD);
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mnrf

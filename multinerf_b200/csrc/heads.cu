@@ -1,0 +1,322 @@
+// Narrow Dense heads (1-4 outputs), bias-gradient column sums, weight repacking, clip+Adam.
+//
+// Heads replace the Dense(1) density head models.py:460, Dense(3) rgb head :585 and the other
+// <=4-wide heads (:495,515,518,521); they are HBM-bound row reductions (one warp per row,
+// 16-byte loads), not GEMM-shaped work.  Optimizer: train_utils.clip_gradients
+// train_utils.py:200-218 + nan_to_num :328 + optax.adam (restated, see oracle/o_train.py).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mnrf {
+
+constexpr int kMaxHead = 4;
+
+// raw[m, o] = sum_k x[m,k] * w[o,k] + b[o]
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(int64_t M, int K, int n_out, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                const __nv_bfloat16* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ raw) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(smraw);   // [n_out][K]
+  for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t m = (int64_t)blockIdx.x * nw + wib; m < M; m += (int64_t)gridDim.x * nw) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + m * ldx);
+    float acc[kMaxHead] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < K / 8; c += 32) {
+      uint4 v = xr[c];
+      uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int o = 0; o < kMaxHead; ++o) {
+        if (o < n_out) {
+          const uint4 wv = reinterpret_cast<const uint4*>(sw + (size_t)o * K)[c];
+          uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            acc[o] += bf16_lo(vv[q]) * bf16_lo(ww[q]) + bf16_hi(vv[q]) * bf16_hi(ww[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < kMaxHead; ++o) {
+      if (o < n_out) {
+        float s = warp_sum(acc[o]);
+        if (lane == 0) raw[m * n_out + o] = s + (b ? b[o] : 0.f);
+      }
+    }
+  }
+}
+
+// dx[m,k] = relu'(x[m,k]) * sum_o draw[m,o] w[o,k];  dw[o,k] += sum_m draw[m,o] x[m,k];  db[o] += sum_m draw[m,o]
+template <int N_OUT, int kMaxChunks>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                const __nv_bfloat16* __restrict__ w, const float* __restrict__ draw,
+                __nv_bfloat16* __restrict__ dx, int64_t lddx, int relu_mask,
+                float* __restrict__ dw, float* __restrict__ db, int64_t rows_per_block) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int n_out = N_OUT;
+  float* sdw = reinterpret_cast<float*>(smraw);                                   // [n_out][K] fp32
+  __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(sdw + (size_t)n_out * K);  // [n_out][K]
+  for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m_end = min(M, m_begin + rows_per_block);
+  // Each lane owns the 8-column chunks c = lane, lane+32, ...: it accumulates their dw in
+  // registers across the rows of this warp and flushes once into shared memory.
+  float racc[N_OUT][kMaxChunks][8];
+#pragma unroll
+  for (int o = 0; o < N_OUT; ++o)
+#pragma unroll
+    for (int q = 0; q < kMaxChunks; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) racc[o][q][e] = 0.f;
+  float dbacc[N_OUT];
+#pragma unroll
+  for (int o = 0; o < N_OUT; ++o) dbacc[o] = 0.f;
+  for (int64_t m = m_begin + wib; m < m_end; m += nw) {
+    float g[N_OUT];
+#pragma unroll
+    for (int o = 0; o < N_OUT; ++o) g[o] = draw[m * n_out + o];
+    const uint4* xr = reinterpret_cast<const uint4*>(x + m * ldx);
+    uint4* dxr = dx ? reinterpret_cast<uint4*>(dx + m * lddx) : nullptr;
+#pragma unroll
+    for (int q = 0; q < kMaxChunks; ++q) {
+      int c = lane + 32 * q;
+      if (c < K / 8) {
+        uint4 v = xr[c];
+        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        float xe[8], de[8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { xe[2 * p] = bf16_lo(vv[p]); xe[2 * p + 1] = bf16_hi(vv[p]); }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) de[e] = 0.f;
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) {
+          const uint4 wv = reinterpret_cast<const uint4*>(sw + (size_t)o * K)[c];
+          uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            de[2 * p] += g[o] * bf16_lo(ww[p]);
+            de[2 * p + 1] += g[o] * bf16_hi(ww[p]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) racc[o][q][e] += g[o] * xe[e];
+        }
+        if (dxr) {
+          if (relu_mask) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) de[e] = xe[e] > 0.f ? de[e] : 0.f;
+          }
+          uint4 o4;
+          o4.x = pack_bf16(de[0], de[1]); o4.y = pack_bf16(de[2], de[3]);
+          o4.z = pack_bf16(de[4], de[5]); o4.w = pack_bf16(de[6], de[7]);
+          dxr[c] = o4;
+        }
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < N_OUT; ++o) dbacc[o] += g[o];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < N_OUT; ++o) {
+#pragma unroll
+    for (int q = 0; q < kMaxChunks; ++q) {
+      int c = lane + 32 * q;
+      if (c < K / 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&sdw[(size_t)o * K + c * 8 + e], racc[o][q][e]);
+      }
+    }
+    if (lane == 0 && db && dbacc[o] != 0.f) atomicAdd(&db[o], dbacc[o]);
+  }
+  __syncthreads();
+  if (dw) for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+}
+
+// out[n] += sum_m x[m, n]
+__global__ void __launch_bounds__(256)
+colsum_kernel(int64_t M, int N, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+              float* __restrict__ out, int64_t rows_per_block) {
+  // thread t owns columns [8t, 8t+8) (16-byte loads); blockDim.x * 8 >= N is enforced by the
+  // launcher through a 2-D grid over column slabs.
+  const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (col >= N) return;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t m = m0; m < m1; ++m) {
+    uint4 v = *reinterpret_cast<const uint4*>(x + m * ldx + col);
+    uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { acc[2 * p] += bf16_lo(vv[p]); acc[2 * p + 1] += bf16_hi(vv[p]); }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) atomicAdd(&out[col + e], acc[e]);
+}
+
+__global__ void pack_weights_kernel(int in_pad, int out, const float* __restrict__ master,
+                                    __nv_bfloat16* __restrict__ w_nk, __nv_bfloat16* __restrict__ w_kn) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int k = k0 + r, n = n0 + threadIdx.x;
+    float v = (k < in_pad && n < out) ? master[(size_t)k * out + n] : 0.f;
+    tile[r][threadIdx.x] = v;
+    if (w_kn && k < in_pad && n < out) w_kn[(size_t)k * out + n] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int n = n0 + r, k = k0 + threadIdx.x;
+    if (w_nk && n < out && k < in_pad) w_nk[(size_t)n * in_pad + k] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+grad_norm_kernel(int64_t n, const float* __restrict__ g, float scale, float max_val,
+                 float* __restrict__ norm_sq) {
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g[i] * scale;
+    if (max_val > 0.f) v = fminf(fmaxf(v, -max_val), max_val);
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(norm_sq, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(mnrf_adam_desc d, float* __restrict__ p, const float* __restrict__ g,
+                 float* __restrict__ mu, float* __restrict__ nu, const float* __restrict__ norm_sq) {
+  float mult = 1.f;
+  if (d.grad_max_norm > 0.f) mult = fminf(1.f, d.grad_max_norm / (kEps + sqrtf(*norm_sq)));
+  const float bc1 = 1.f - powf(d.beta1, (float)d.step);
+  const float bc2 = 1.f - powf(d.beta2, (float)d.step);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g[i] * d.grad_scale;
+    if (d.grad_max_val > 0.f) v = fminf(fmaxf(v, -d.grad_max_val), d.grad_max_val);
+    v *= mult;
+    // jnp.nan_to_num: nan -> 0, +-inf -> +-max float
+    if (isnan(v)) v = 0.f;
+    else if (isinf(v)) v = v > 0.f ? 3.4028235e38f : -3.4028235e38f;
+    float m = d.beta1 * mu[i] + (1.f - d.beta1) * v;
+    float s = d.beta2 * nu[i] + (1.f - d.beta2) * v * v;
+    mu[i] = m;
+    nu[i] = s;
+    float mh = m / bc1, sh = s / bc2;
+    p[i] = p[i] - d.lr * mh / (sqrtf(sh) + d.eps);
+  }
+}
+
+}  // namespace mnrf
+
+extern "C" int mnrf_head_fwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
+                             const mnrf_bf16* w, const float* b, float* raw, mnrf_stream stream) {
+  using namespace mnrf;
+  MNRF_CHECK(x && w && raw, "mnrf_head_fwd: null pointer");
+  MNRF_CHECK(n_out >= 1 && n_out <= kMaxHead, "mnrf_head_fwd: n_out %d not in [1,4]", n_out);
+  MNRF_CHECK(k % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0,
+             "mnrf_head_fwd: K/ld must be multiples of 8 and pointers 16-byte aligned");
+  if (m == 0) return 0;
+  size_t smem = (size_t)n_out * k * 2;
+  int blocks = (int)std::min<int64_t>((m + 7) / 8, (int64_t)mnrf_num_sms() * 8);
+  head_fwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
+      m, k, n_out, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+      reinterpret_cast<const __nv_bfloat16*>(w), b, raw);
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
+                             const mnrf_bf16* w, const float* draw, mnrf_bf16* dx, int64_t lddx,
+                             int32_t relu_mask, float* dw, float* db, mnrf_stream stream) {
+  using namespace mnrf;
+  MNRF_CHECK(x && w && draw, "mnrf_head_bwd: null pointer");
+  MNRF_CHECK(n_out >= 1 && n_out <= kMaxHead, "mnrf_head_bwd: n_out %d not in [1,4]", n_out);
+  MNRF_CHECK(k % 8 == 0 && k <= 1536 && ldx % 8 == 0 && (!dx || lddx % 8 == 0),
+             "mnrf_head_bwd: K must be a multiple of 8 and <= 1536");
+  if (m == 0) return 0;
+  size_t smem = (size_t)n_out * k * (4 + 2);
+  MNRF_CHECK(smem <= 48 * 1024, "mnrf_head_bwd: n_out*K too large for the shared-memory staging");
+  int blocks = (int)std::min<int64_t>((m + 7) / 8, (int64_t)mnrf_num_sms() * 4);
+  int64_t rpb = (m + blocks - 1) / blocks;
+  const int chunks = (k / 8 + 31) / 32;
+#define MNRF_HB(NO, CK)                                                                         \
+  head_bwd_kernel<NO, CK><<<blocks, 256, smem, (cudaStream_t)stream>>>(                         \
+      m, k, reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(w), \
+      draw, reinterpret_cast<__nv_bfloat16*>(dx), lddx, relu_mask, dw, db, rpb)
+#define MNRF_HB_N(NO)                                      \
+  do {                                                     \
+    if (chunks <= 1) MNRF_HB(NO, 1);                       \
+    else if (chunks <= 2) MNRF_HB(NO, 2);                  \
+    else if (chunks <= 4) MNRF_HB(NO, 4);                  \
+    else MNRF_HB(NO, 6);                                   \
+  } while (0)
+  switch (n_out) {
+    case 1: MNRF_HB_N(1); break;
+    case 2: MNRF_HB_N(2); break;
+    case 3: MNRF_HB_N(3); break;
+    default: MNRF_HB_N(4); break;
+  }
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mnrf_colsum(int64_t m, int32_t n, const mnrf_bf16* x, int64_t ldx, float* out,
+                           mnrf_stream stream) {
+  using namespace mnrf;
+  MNRF_CHECK(x && out, "mnrf_colsum: null pointer");
+  MNRF_CHECK(n % 8 == 0 && ldx % 8 == 0, "mnrf_colsum: N and ld must be multiples of 8");
+  if (m == 0) return 0;
+  const int threads = 128;
+  dim3 grid;
+  grid.y = (n / 8 + threads - 1) / threads;
+  int bx = std::max(1, mnrf_num_sms() * 8 / (int)grid.y);
+  bx = (int)std::min<int64_t>(bx, (m + 63) / 64);
+  grid.x = bx;
+  int64_t rpb = (m + bx - 1) / bx;
+  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+      m, n, reinterpret_cast<const __nv_bfloat16*>(x), ldx, out, rpb);
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mnrf_pack_weights(int32_t in_pad, int32_t out, const float* master, mnrf_bf16* w_nk,
+                                 mnrf_bf16* w_kn, mnrf_stream stream) {
+  using namespace mnrf;
+  MNRF_CHECK(master, "mnrf_pack_weights: null pointer");
+  dim3 grid((out + 31) / 32, (in_pad + 31) / 32), block(32, 8);
+  pack_weights_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      in_pad, out, master, reinterpret_cast<__nv_bfloat16*>(w_nk), reinterpret_cast<__nv_bfloat16*>(w_kn));
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mnrf_clip_adam(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
+                              float* nu, float* norm_sq_scratch, mnrf_stream stream) {
+  using namespace mnrf;
+  MNRF_CHECK(d && params && grads && mu && nu && norm_sq_scratch, "mnrf_clip_adam: null pointer");
+  MNRF_CHECK(d->step >= 1, "mnrf_clip_adam: step is the 1-based update count");
+  if (d->n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = (int)std::min<int64_t>((d->n + 255) / 256, (int64_t)mnrf_num_sms() * 8);
+  MNRF_CUDA(cudaMemsetAsync(norm_sq_scratch, 0, sizeof(float), s));
+  if (d->grad_max_norm > 0.f) {
+    grad_norm_kernel<<<blocks, 256, 0, s>>>(d->n, grads, d->grad_scale, d->grad_max_val, norm_sq_scratch);
+    MNRF_LAUNCH_CHECK();
+  }
+  clip_adam_kernel<<<blocks, 256, 0, s>>>(*d, params, grads, mu, nu, norm_sq_scratch);
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,206 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per entry point).
+
+These mirror the reference's free functions where one exists (stepfun.sample_intervals,
+render.cast_rays + coord.integrated_pos_enc, render.compute_alpha_weights +
+volumetric_rendering, ...) but operate on flat [B, ...] CUDA tensors.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as L
+
+EPS = float(torch.finfo(torch.float32).eps)
+
+
+def _f32(t):
+  assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), 'need contiguous fp32'
+  return t
+
+
+def u_grid(num_samples, randomized):
+  """Host-side u grid of stepfun.sample (stepfun.py:190-209): (u_base[S] fp32, max_jitter)."""
+  eps = EPS
+  if not randomized:
+    pad = 1 / (2 * num_samples)
+    return torch.linspace(pad, 1.0 - pad - eps, num_samples, dtype=torch.float32), 0.0
+  u_max = eps + (1 - eps) / num_samples
+  max_jitter = (1 - u_max) / (num_samples - 1) - eps
+  return torch.linspace(0, 1 - u_max, num_samples, dtype=torch.float32), max_jitter
+
+
+def sample_level(sdist_prev, w_prev, num_samples, *, dilation=0.0, use_dilation=False,
+                 domain=(0.0, 1.0), anneal=1.0, resample_padding=0.0, jitter=None,
+                 single_jitter=True, u_base=None, max_jitter=None, cw_in=None, want_index=False,
+                 want_debug=False, out=None):
+  """One level of hierarchical resampling -> sdist [B, S+1] (+ int32 idx, debug arrays)."""
+  lib = L.load()
+  if num_samples <= 1:
+    raise ValueError(f'num_samples must be > 1, is {num_samples}.')
+  B, P = w_prev.shape
+  assert sdist_prev.shape == (B, P + 1)
+  dev = sdist_prev.device
+  if u_base is None:
+    ub, mj = u_grid(num_samples, jitter is not None)
+    u_base = ub.to(dev)
+    max_jitter = mj if max_jitter is None else max_jitter
+  d = L.SampleDesc(B, P, num_samples, int(use_dilation), float(dilation), float(domain[0]),
+                   float(domain[1]), float(anneal), float(resample_padding),
+                   0 if jitter is None else (1 if single_jitter else 2), float(max_jitter or 0.0))
+  nb = 3 * P - 2 if use_dilation else P
+  sdist = out if out is not None else torch.empty(B, num_samples + 1, device=dev)
+  idx = torch.empty(B, num_samples, device=dev, dtype=torch.int32) if want_index else None
+  cw = torch.empty(B, nb + 1, device=dev) if want_debug else None
+  tdil = torch.empty(B, nb + 1, device=dev) if want_debug else None
+  wdil = torch.empty(B, nb, device=dev) if want_debug else None
+  L.check(lib.mnrf_sample_level(C.byref(d), L.ptr(_f32(sdist_prev)), L.ptr(_f32(w_prev)),
+                                L.ptr(_f32(u_base)), L.ptr(_f32(jitter)), L.ptr(_f32(cw_in)),
+                                L.ptr(sdist), L.ptr(idx), L.ptr(cw), L.ptr(tdil), L.ptr(wdil),
+                                L.stream_ptr()))
+  if want_index or want_debug:
+    return sdist, dict(idx=idx, cw=cw, tdil=tdil, wdil=wdil)
+  return sdist
+
+
+def encode(sdist, origins, directions, radii, near, far, basis, *, min_deg, max_deg,
+           raydist_fn=None, ray_shape='cone', warp_contract=False, disable_integration=False,
+           feat=None, feat_cols=None, want_f32=False, want_tdist=False):
+  """cast_rays + (contract) + lift + IPE -> bf16 features [B*S, ld] (row stride from `feat`)."""
+  lib = L.load()
+  if ray_shape not in L.RAY_SHAPE:
+    raise ValueError("ray_shape must be 'cone' or 'cylinder'")
+  B, S1 = sdist.shape
+  S = S1 - 1
+  K = basis.shape[0]
+  F = 2 * K * (max_deg - min_deg)
+  if feat_cols is None:
+    feat_cols = (F + 63) // 64 * 64
+  if feat is None:
+    feat = torch.empty(B * S, feat_cols, device=sdist.device, dtype=torch.bfloat16)
+  assert feat.dtype == torch.bfloat16 and feat.stride(1) == 1
+  ld = feat.stride(0)
+  d = L.EncodeDesc(B, S, L.RAYDIST[raydist_fn], L.RAY_SHAPE[ray_shape], int(warp_contract),
+                   int(disable_integration), K, min_deg, max_deg, ld, feat_cols)
+  f32 = torch.empty(B * S, F, device=sdist.device) if want_f32 else None
+  tdist = torch.empty(B, S + 1, device=sdist.device) if want_tdist else None
+  L.check(lib.mnrf_encode(C.byref(d), L.ptr(_f32(sdist)), L.ptr(_f32(origins)),
+                          L.ptr(_f32(directions)), L.ptr(_f32(radii)), L.ptr(_f32(near)),
+                          L.ptr(_f32(far)), L.ptr(_f32(basis)), L.ptr(feat), L.ptr(f32),
+                          L.ptr(tdist), L.stream_ptr()))
+  return feat, f32, tdist
+
+
+def viewdir_enc(viewdirs, num_samples, deg, out, col0, col_end):
+  lib = L.load()
+  B = viewdirs.shape[0]
+  L.check(lib.mnrf_viewdir_enc(B, num_samples, deg, L.ptr(_f32(viewdirs)), L.ptr(out),
+                               out.stride(0), col0, col_end, L.stream_ptr()))
+
+
+def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv=None, mask=None,
+         impl=0):
+  """Dense-layer GEMM (see include/mnrf.h).  a/b/out/mask are 2-D views with unit inner stride."""
+  lib = L.load()
+  for t in (a, b, out) + ((mask,) if mask is not None else ()):
+    assert t.stride(-1) == 1
+  d = L.GemmDesc(mode, act, m, n, k, a.stride(0), b.stride(0), out.stride(0),
+                 mask.stride(0) if mask is not None else 0, impl)
+  L.check(lib.mnrf_gemm(C.byref(d), L.ptr(a), L.ptr(b), L.ptr(bias), L.ptr(rowv), L.ptr(colv),
+                        L.ptr(mask), L.ptr(out), L.stream_ptr()))
+  return out
+
+
+def head_fwd(x, w_nk, bias, n_out, k, raw=None):
+  lib = L.load()
+  M = x.shape[0]
+  if raw is None:
+    raw = torch.empty(M, n_out, device=x.device)
+  L.check(lib.mnrf_head_fwd(M, k, n_out, L.ptr(x), x.stride(0), L.ptr(w_nk), L.ptr(bias),
+                            L.ptr(raw), L.stream_ptr()))
+  return raw
+
+
+def head_bwd(x, w_nk, draw, n_out, k, dx=None, relu_mask=False, dw=None, db=None):
+  lib = L.load()
+  M = x.shape[0]
+  L.check(lib.mnrf_head_bwd(M, k, n_out, L.ptr(x), x.stride(0), L.ptr(w_nk), L.ptr(_f32(draw)),
+                            L.ptr(dx), dx.stride(0) if dx is not None else 0, int(relu_mask),
+                            L.ptr(dw), L.ptr(db), L.stream_ptr()))
+
+
+def colsum(x, n, out):
+  lib = L.load()
+  L.check(lib.mnrf_colsum(x.shape[0], n, L.ptr(x), x.stride(0), L.ptr(out), L.stream_ptr()))
+
+
+def _cdesc(B, S, *, raydist_fn, opaque_background, density_bias, density_noise, rgb_activation,
+           rgb_premultiplier, rgb_bias, rgb_padding, bg_const):
+  if rgb_activation not in L.RGB_ACT:
+    raise ValueError(f'rgb_activation {rgb_activation!r} not supported by the CUDA path')
+  return L.CompositeDesc(B, S, L.RAYDIST[raydist_fn], int(opaque_background), float(density_bias),
+                         float(density_noise), L.RGB_ACT[rgb_activation], float(rgb_premultiplier),
+                         float(rgb_bias), float(rgb_padding), float(bg_const))
+
+
+def composite_fwd(raw_density, raw_rgb, sdist, directions, near, far, *, cfg, density_noise=None,
+                  bg_rgb=None, want_samples=False, want_extras=False):
+  """compute_alpha_weights + volumetric_rendering.  cfg: kwargs of _cdesc."""
+  lib = L.load()
+  B, S = raw_density.shape
+  dev = raw_density.device
+  d = _cdesc(B, S, **cfg)
+  weights = torch.empty(B, S, device=dev)
+  rgb = torch.empty(B, 3, device=dev)
+  dens = torch.empty(B, S, device=dev) if want_samples else None
+  rgbs = torch.empty(B, S, 3, device=dev) if want_samples else None
+  acc = torch.empty(B, device=dev) if want_extras else None
+  dist = torch.empty(B, 4, device=dev) if want_extras else None
+  L.check(lib.mnrf_composite_fwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
+                                 L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
+                                 L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
+                                 L.ptr(_f32(bg_rgb)), L.ptr(weights), L.ptr(rgb), L.ptr(dens),
+                                 L.ptr(rgbs), L.ptr(acc), L.ptr(dist), L.stream_ptr()))
+  return dict(weights=weights, rgb=rgb, density=dens, rgb_samples=rgbs, acc=acc, dist=dist)
+
+
+def composite_bwd(raw_density, raw_rgb, sdist, directions, near, far, target_rgb, lossmult,
+                  inv_denom, stats, *, cfg, loss_type, charb_padding, data_mult, distortion_mult,
+                  interlevel_mult, sdist_fine=None, weights_fine=None, density_noise=None,
+                  bg_rgb=None, d_raw_density=None, d_raw_rgb=None):
+  lib = L.load()
+  B, S = raw_density.shape
+  dev = raw_density.device
+  Sf = sdist_fine.shape[1] - 1 if sdist_fine is not None else 0
+  d = L.LossDesc(_cdesc(B, S, **cfg), L.LOSS_TYPE[loss_type], float(charb_padding), float(data_mult),
+                 float(distortion_mult), float(interlevel_mult), Sf,
+                 lossmult.shape[-1] if lossmult.dim() > 1 else 1)
+  if d_raw_density is None:
+    d_raw_density = torch.empty(B, S, device=dev)
+  if raw_rgb is not None and d_raw_rgb is None:
+    d_raw_rgb = torch.empty(B, S, 3, device=dev)
+  L.check(lib.mnrf_composite_bwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
+                                 L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
+                                 L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
+                                 L.ptr(_f32(bg_rgb)), None, None, L.ptr(_f32(target_rgb)),
+                                 L.ptr(_f32(lossmult)), L.ptr(_f32(inv_denom)),
+                                 L.ptr(_f32(sdist_fine)), L.ptr(_f32(weights_fine)),
+                                 L.ptr(d_raw_density), L.ptr(d_raw_rgb), L.ptr(stats),
+                                 L.stream_ptr()))
+  return d_raw_density, d_raw_rgb
+
+
+def clip_adam(params, grads, mu, nu, scratch, *, step, lr, beta1, beta2, eps, grad_max_val,
+              grad_max_norm, grad_scale=1.0):
+  lib = L.load()
+  d = L.AdamDesc(params.numel(), float(grad_max_val), float(grad_max_norm), float(lr), float(beta1),
+                 float(beta2), float(eps), int(step), float(grad_scale))
+  L.check(lib.mnrf_clip_adam(C.byref(d), L.ptr(params), L.ptr(grads), L.ptr(mu), L.ptr(nu),
+                             L.ptr(scratch), L.stream_ptr()))
+
+
+def pack_weights(master, w_nk, w_kn):
+  lib = L.load()
+  in_pad, out = master.shape
+  L.check(lib.mnrf_pack_weights(in_pad, out, L.ptr(master), L.ptr(w_nk), L.ptr(w_kn),
+                                L.stream_ptr()))
