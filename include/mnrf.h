@@ -129,7 +129,7 @@ int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, c
  * raw[M, n_out] = X[M, K](bf16) * W[n_out, K](bf16) + b, fp32 accumulate; models.py:460,585.
  * Backward: dX[M, K] (bf16, optionally relu-masked by X > 0; optional accumulate is not
  * provided -- the trunk adds the density term through mnrf_gemm's rowv/colv),
- * dW[n_out, K] += , db[n_out] += (fp32 atomics).
+ * dW[K, n_out] += (the fp32 master layout [in, out]), db[n_out] += (fp32 atomics).
  */
 int mnrf_head_fwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
                   const mnrf_bf16* w, const float* b, float* raw, mnrf_stream stream);

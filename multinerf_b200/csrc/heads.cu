@@ -49,7 +49,7 @@ head_fwd_kernel(int64_t M, int K, int n_out, const __nv_bfloat16* __restrict__ x
   }
 }
 
-// dx[m,k] = relu'(x[m,k]) * sum_o draw[m,o] w[o,k];  dw[o,k] += sum_m draw[m,o] x[m,k];  db[o] += sum_m draw[m,o]
+// dx[m,k] = relu'(x[m,k]) * sum_o draw[m,o] w[o,k];  dw[k,o] += sum_m draw[m,o] x[m,k];  db[o] += sum_m draw[m,o]
 template <int N_OUT, int kMaxChunks>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t ldx,
@@ -136,7 +136,11 @@ head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t l
     if (lane == 0 && db && dbacc[o] != 0.f) atomicAdd(&db[o], dbacc[o]);
   }
   __syncthreads();
-  if (dw) for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+  // dw is in the master layout [K, n_out] (row-major), the staging buffer is [n_out][K]
+  if (dw) for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) {
+    int o = i / K, k = i - o * K;
+    atomicAdd(&dw[(size_t)k * n_out + o], sdw[i]);
+  }
 }
 
 // out[n] += sum_m x[m, n]

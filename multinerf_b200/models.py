@@ -1,0 +1,649 @@
+"""Host side of the hot path: `Model.__call__` / `render_image` over the sm_100a kernels.
+
+Keeps the reference's surface (internal/models.py):
+  Model.__call__(rng, rays, train_frac, compute_extras, zero_glo) -> (renderings, ray_history)
+                                                      models.py:75-312
+  construct_model(rng, rays, config) -> (model, variables)    models.py:315-338
+  render_image(render_fn, rays, rng, config)                  models.py:625-706
+Python only orchestrates: per level it launches resample -> cast+IPE -> Dense chain (tcgen05)
+-> heads -> compositing; the backward chain mirrors it (train_utils.py:239-339 closure lives
+in multinerf_b200/train_utils.py).  PyTorch provides device buffers, streams and RNG draws.
+There is no CPU path: constructing a Model without a B200 raises.
+"""
+import dataclasses
+import math
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import configs
+from . import geopoly
+from . import lib as L
+from . import ops
+from . import utils
+
+
+def _pad64(n):
+  return (n + 63) // 64 * 64
+
+
+@dataclasses.dataclass
+class DenseSpec:
+  """One nn.Dense of the reference MLP (creation order = flax auto-name Dense_k)."""
+  name: str
+  role: str            # trunk | density | bottleneck | view | rgb
+  in_dim: int          # logical inputs (flax kernel rows)
+  in_pad: int          # rows of the padded master / K of the GEMM
+  out_dim: int
+  head: bool           # True: narrow head kernel, False: tcgen05 GEMM
+  act: int = L.ACT_NONE
+  # row map: logical flax row -> padded master row (skip-concat / view-input padding)
+  row_map: Optional[np.ndarray] = None
+  w_off: int = 0       # offsets (floats) into the module's flat master buffer
+  b_off: int = 0
+
+
+class MLPPlan:
+  """Static layout of one MLP: layer table, buffer widths, flat parameter offsets."""
+
+  def __init__(self, cfg: configs.MLPConfig, use_viewdirs=True):
+    cfg.validate()
+    unsupported = [k for k in ('use_reflections', 'use_directional_enc', 'enable_pred_roughness',
+                               'use_diffuse_color', 'use_specular_tint', 'use_n_dot_v',
+                               'enable_pred_normals') if getattr(cfg, k)]
+    if unsupported or not cfg.disable_density_normals:
+      raise NotImplementedError(
+          'CUDA path: Ref-NeRF branches (%s, density normals) are a later milestone '
+          '(DESIGN.md scope table)' % ', '.join(unsupported))
+    if cfg.net_activation != 'relu' or cfg.density_activation != 'softplus':
+      raise NotImplementedError('CUDA path supports relu trunk / softplus density')
+    if cfg.bottleneck_noise > 0:
+      raise NotImplementedError('bottleneck_noise is not wired into the CUDA path yet')
+    self.cfg = cfg
+    self.basis = np.ascontiguousarray(
+        geopoly.generate_basis(cfg.basis_shape, cfg.basis_subdivisions), dtype=np.float32)
+    self.K = self.basis.shape[0]
+    self.L = cfg.max_deg_point - cfg.min_deg_point
+    self.F = 2 * self.K * self.L
+    self.Fpad = _pad64(self.F)
+    W = cfg.net_width
+    assert W % 64 == 0, 'net_width must be a multiple of 64'
+    specs: List[DenseSpec] = []
+    k = 0
+    x_dim, x_pad, x_has_feat = self.F, self.Fpad, False
+    self.trunk_in = []        # per trunk layer: (width part, has concatenated features)
+    self.concat_after = []    # trunk layers whose output is concatenated with the features
+    for i in range(cfg.net_depth):
+      rm = None
+      if x_has_feat:
+        rm = np.concatenate([np.arange(W), W + np.arange(self.F)])
+      specs.append(DenseSpec(f'Dense_{k}', 'trunk', x_dim, x_pad, W, False, L.ACT_RELU, rm))
+      k += 1
+      if i % cfg.skip_layer == 0 and i > 0:
+        self.concat_after.append(i)
+        x_dim, x_pad, x_has_feat = W + self.F, W + self.Fpad, True
+      else:
+        x_dim, x_pad, x_has_feat = W, W, False
+    self.last_has_feat = x_has_feat
+    rm = np.concatenate([np.arange(W), W + np.arange(self.F)]) if x_has_feat else None
+    specs.append(DenseSpec(f'Dense_{k}', 'density', x_dim, x_pad, 1, True, row_map=rm))
+    k += 1
+    self.has_rgb = not cfg.disable_rgb
+    self.use_viewdirs = use_viewdirs
+    if self.has_rgb:
+      if not use_viewdirs:
+        raise NotImplementedError('use_viewdirs=False with rgb is not wired into the CUDA path')
+      if cfg.bottleneck_width <= 0:
+        raise NotImplementedError('bottleneck_width == 0 is not supported (models.py:536-554)')
+      bw = cfg.bottleneck_width
+      assert bw % 64 == 0
+      specs.append(DenseSpec(f'Dense_{k}', 'bottleneck', x_dim, x_pad, bw, False, L.ACT_NONE, rm))
+      k += 1
+      self.dir_dim = 3 + 6 * cfg.deg_view
+      vin, vin_pad = bw + self.dir_dim, _pad64(bw + self.dir_dim)
+      self.vin_dim, self.vin_pad = vin, vin_pad
+      Wv = cfg.net_width_viewdirs
+      assert Wv % 64 == 0
+      v_dim, v_pad, v_has_in = vin, vin_pad, True
+      self.view_concat_after = []
+      for i in range(cfg.net_depth_viewdirs):
+        if i == 0:
+          rmv = None
+        elif v_has_in:
+          rmv = np.concatenate([np.arange(Wv), Wv + np.arange(vin)])
+        else:
+          rmv = None
+        specs.append(DenseSpec(f'Dense_{k}', 'view', v_dim, v_pad, Wv, False, L.ACT_RELU, rmv))
+        k += 1
+        if i % cfg.skip_layer_dir == 0 and i > 0:
+          self.view_concat_after.append(i)
+          v_dim, v_pad, v_has_in = Wv + vin, Wv + vin_pad, True
+        else:
+          v_dim, v_pad, v_has_in = Wv, Wv, False
+      if self.view_concat_after:
+        raise NotImplementedError('skip connections inside the view MLP (net_depth_viewdirs > 4)')
+      specs.append(DenseSpec(f'Dense_{k}', 'rgb', v_dim, v_pad, cfg.num_rgb_channels, True))
+      k += 1
+    off = 0
+    for s in specs:
+      s.w_off = off
+      off += s.in_pad * s.out_dim
+      off = (off + 3) // 4 * 4
+      s.b_off = off
+      off += s.out_dim
+      off = (off + 3) // 4 * 4
+    self.specs = specs
+    self.flat_size = off
+    self.num_params = sum(s.in_dim * s.out_dim + s.out_dim for s in specs)
+
+  def by_role(self, role):
+    return [s for s in self.specs if s.role == role]
+
+
+class MLPDevice:
+  """Device state of one MLP: fp32 master slice, bf16 shadows, gradient views."""
+
+  def __init__(self, plan: MLPPlan, master, grads, device):
+    self.plan = plan
+    self.master, self.grads = master, grads           # views into the global flat buffers
+    self.device = device
+    self.basis = torch.tensor(plan.basis, device=device)
+    self.w_nk, self.w_kn, self.colv = {}, {}, {}
+    for s in plan.specs:
+      self.w_nk[s.name] = torch.zeros(s.out_dim, s.in_pad, device=device, dtype=torch.bfloat16)
+      if not s.head:
+        self.w_kn[s.name] = torch.zeros(s.in_pad, s.out_dim, device=device, dtype=torch.bfloat16)
+    self.repack()
+
+  def W(self, s, buf=None):
+    buf = self.master if buf is None else buf
+    return buf[s.w_off:s.w_off + s.in_pad * s.out_dim].view(s.in_pad, s.out_dim)
+
+  def b(self, s, buf=None):
+    buf = self.master if buf is None else buf
+    return buf[s.b_off:s.b_off + s.out_dim]
+
+  def repack(self):
+    """fp32 master -> bf16 operand layouts (after init and after every optimizer step)."""
+    for s in self.plan.specs:
+      ops.pack_weights(self.W(s), self.w_nk[s.name], self.w_kn.get(s.name))
+    d = self.plan.by_role('density')[0]
+    self.colv_density = self.w_nk[d.name][0].float().contiguous()   # bf16-rounded, as the fwd used
+
+
+class LevelState:
+  """Per-level device buffers kept from forward for the backward pass."""
+  pass
+
+
+class Params:
+  """`variables`: flat fp32 parameter/gradient/Adam buffers + per-module views."""
+
+  def __init__(self, plans: Dict[str, MLPPlan], device, extra: Dict[str, int]):
+    self.plans = plans
+    self.offsets = {}
+    off = 0
+    for name, plan in plans.items():
+      self.offsets[name] = (off, plan.flat_size)
+      off += plan.flat_size
+    for name, n in extra.items():
+      self.offsets[name] = (off, n)
+      off += (n + 3) // 4 * 4
+    self.total = off
+    self.flat = torch.zeros(off, device=device)
+    self.grads = torch.zeros(off, device=device)
+    self.mu = torch.zeros(off, device=device)
+    self.nu = torch.zeros(off, device=device)
+    self.step = 0
+
+  def seg(self, name, buf=None):
+    o, n = self.offsets[name]
+    return (self.flat if buf is None else buf)[o:o + n]
+
+
+def _init_kernel(rng, name, fan_in, fan_out):
+  """flax initialisers (he_uniform / glorot_uniform ...) restated; host numpy.  PARITY UNPINNED:
+  threefry streams cannot be reproduced, only the distribution."""
+  if name == 'he_uniform':
+    lim = math.sqrt(6.0 / fan_in)
+    return rng.uniform(-lim, lim, (fan_in, fan_out)).astype(np.float32)
+  if name == 'glorot_uniform':
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, (fan_in, fan_out)).astype(np.float32)
+  if name == 'he_normal':
+    return (rng.standard_normal((fan_in, fan_out)) * math.sqrt(2.0 / fan_in) / .87962566103423978
+            ).clip(-2 * math.sqrt(2.0 / fan_in) / .87962566103423978,
+                   2 * math.sqrt(2.0 / fan_in) / .87962566103423978).astype(np.float32)
+  if name == 'glorot_normal':
+    return (rng.standard_normal((fan_in, fan_out)) * math.sqrt(2.0 / (fan_in + fan_out))
+            ).astype(np.float32)
+  raise ValueError(f'unknown weight_init {name!r}')
+
+
+class Model:
+  """The mip-NeRF 360 model (reference class `Model`, internal/models.py:47-312)."""
+
+  def __init__(self, bundle: configs.Bundle, device=None):
+    L.require_device()
+    self.bundle = bundle
+    self.config = bundle.config
+    self.mcfg = bundle.model
+    m = self.mcfg
+    self.device = torch.device(device if device is not None else torch.device('cuda', torch.cuda.current_device()))
+    for f in dataclasses.fields(m):            # expose Model.<field> like the reference
+      setattr(self, f.name, getattr(m, f.name))
+    if m.num_glo_features > 0:
+      raise NotImplementedError('GLO embeddings are not wired into the CUDA path yet')
+    if m.learned_exposure_scaling:
+      raise NotImplementedError('learned_exposure_scaling (RawNeRF) is a later milestone')
+    if m.bg_intensity_range[0] != m.bg_intensity_range[1]:
+      raise NotImplementedError('random background colours are not wired into the CUDA path yet')
+    if m.ray_shape not in L.RAY_SHAPE:
+      raise ValueError("ray_shape must be 'cone' or 'cylinder'")
+    if m.raydist_fn not in L.RAYDIST:
+      raise ValueError(f'raydist_fn {m.raydist_fn!r} not supported')
+    if not m.stop_level_grad:
+      raise NotImplementedError('stop_level_grad=False (gradients through resampling)')
+    self.plans = {'NerfMLP_0': MLPPlan(bundle.nerf_mlp, m.use_viewdirs)}
+    if not m.single_mlp:
+      self.plans['PropMLP_0'] = MLPPlan(bundle.prop_mlp, m.use_viewdirs)
+    self.params: Optional[Params] = None
+    self.mlps: Dict[str, MLPDevice] = {}
+    self._levels: Dict[Any, LevelState] = {}
+    self._u_cache = {}
+
+  # ------------------------------------------------------------------ parameters
+  def num_params(self):
+    return sum(p.num_params for p in self.plans.values())
+
+  def init(self, seed=0, flax_params=None):
+    """Creates `variables` (random init like flax, or from a flax-style tree of arrays)."""
+    params = Params(self.plans, self.device, {})
+    rng = np.random.default_rng(seed)
+    host = np.zeros(params.total, np.float32)
+    for mname, plan in self.plans.items():
+      o, _ = params.offsets[mname]
+      for s in plan.specs:
+        if flax_params is not None:
+          kern = np.asarray(flax_params[mname][s.name]['kernel'], np.float32)
+          bias = np.asarray(flax_params[mname][s.name]['bias'], np.float32)
+          if kern.shape != (s.in_dim, s.out_dim):
+            raise ValueError(f'{mname}/{s.name}: kernel {kern.shape} != {(s.in_dim, s.out_dim)}')
+        else:
+          kern = _init_kernel(rng, plan.cfg.weight_init, s.in_dim, s.out_dim)
+          bias = np.zeros(s.out_dim, np.float32)
+        Wp = np.zeros((s.in_pad, s.out_dim), np.float32)
+        rows = s.row_map if s.row_map is not None else np.arange(s.in_dim)
+        Wp[rows] = kern
+        host[o + s.w_off:o + s.w_off + Wp.size] = Wp.reshape(-1)
+        host[o + s.b_off:o + s.b_off + s.out_dim] = bias
+    params.flat.copy_(torch.from_numpy(host))
+    self.bind(params)
+    return params
+
+  def bind(self, params: Params):
+    self.params = params
+    self.mlps = {n: MLPDevice(p, params.seg(n), params.seg(n, params.grads), self.device)
+                 for n, p in self.plans.items()}
+
+  def export_flax(self):
+    """Parameters as the reference's flax tree (numpy), dropping the padding rows."""
+    out = {}
+    for mname, plan in self.plans.items():
+      mlp = self.mlps[mname]
+      out[mname] = {}
+      for s in plan.specs:
+        Wp = mlp.W(s).detach().cpu().numpy()
+        rows = s.row_map if s.row_map is not None else np.arange(s.in_dim)
+        out[mname][s.name] = {'kernel': Wp[rows].copy(), 'bias': mlp.b(s).detach().cpu().numpy().copy()}
+    return out
+
+  def export_grads_flax(self):
+    out = {}
+    for mname, plan in self.plans.items():
+      mlp = self.mlps[mname]
+      out[mname] = {}
+      for s in plan.specs:
+        Wp = mlp.W(s, mlp.grads).detach().cpu().numpy()
+        rows = s.row_map if s.row_map is not None else np.arange(s.in_dim)
+        out[mname][s.name] = {'kernel': Wp[rows].copy(),
+                              'bias': mlp.b(s, mlp.grads).detach().cpu().numpy().copy()}
+    return out
+
+  # ------------------------------------------------------------------ schedule
+  def level_schedule(self, train_frac):
+    m = self.mcfg
+    init_s_near = 0.0
+    if m.near_anneal_rate is not None:
+      init_s_near = min(max(1 - train_frac / m.near_anneal_rate, 0.0), m.near_anneal_init)
+    init_s_far = 1.0
+    prod = 1
+    out = []
+    for i in range(m.num_levels):
+      is_prop = i < m.num_levels - 1
+      ns = m.num_prop_samples if is_prop else m.num_nerf_samples
+      dilation = m.dilation_bias + m.dilation_multiplier * (init_s_far - init_s_near) / prod
+      prod *= ns
+      use_dil = (m.dilation_bias > 0 or m.dilation_multiplier > 0) and i > 0
+      if m.anneal_slope > 0:
+        s = m.anneal_slope
+        anneal = (s * train_frac) / ((s - 1) * train_frac + 1)
+      else:
+        anneal = 1.0
+      out.append(dict(is_prop=is_prop, S=ns, dilation=dilation, use_dilation=use_dil, anneal=anneal))
+    return init_s_near, init_s_far, out
+
+  def _u(self, S, randomized):
+    key = (S, randomized)
+    if key not in self._u_cache:
+      ub, mj = ops.u_grid(S, randomized)
+      self._u_cache[key] = (ub.to(self.device), mj)
+    return self._u_cache[key]
+
+  def _comp_cfg(self, cfg):
+    return dict(raydist_fn=self.mcfg.raydist_fn, opaque_background=self.mcfg.opaque_background,
+                density_bias=cfg.density_bias, density_noise=cfg.density_noise,
+                rgb_activation=cfg.rgb_activation, rgb_premultiplier=cfg.rgb_premultiplier,
+                rgb_bias=cfg.rgb_bias, rgb_padding=cfg.rgb_padding,
+                bg_const=self.mcfg.bg_intensity_range[0])
+
+  # ------------------------------------------------------------------ buffers
+  def _level_state(self, key, mname, B, S):
+    st = self._levels.get(key)
+    plan = self.plans[mname]
+    if st is not None and st.B == B and st.S == S and st.mname == mname:
+      return st
+    st = LevelState()
+    st.B, st.S, st.mname = B, S, mname
+    M = B * S
+    dev = self.device
+    W = plan.cfg.net_width
+    bf = torch.bfloat16
+    st.sdist = torch.empty(B, S + 1, device=dev)
+    # trunk activations; the layer whose output is concatenated with the features owns the
+    # feature columns (encode writes there), otherwise features get their own buffer
+    st.acts = []
+    for i in range(plan.cfg.net_depth):
+      width = W + plan.Fpad if i in plan.concat_after else W
+      st.acts.append(torch.empty(M, width, device=dev, dtype=bf))
+    if plan.concat_after:
+      st.feat = st.acts[plan.concat_after[0]][:, W:]
+      st.feat_copies = [st.acts[i][:, W:] for i in plan.concat_after[1:]]
+    else:
+      st.feat = torch.empty(M, plan.Fpad, device=dev, dtype=bf)
+      st.feat_copies = []
+    st.raw_density = torch.empty(B, S, device=dev)
+    st.d_raw_density = torch.empty(B, S, device=dev)
+    if plan.has_rgb:
+      st.vin = torch.empty(M, plan.vin_pad, device=dev, dtype=bf)
+      st.vacts = [torch.empty(M, plan.cfg.net_width_viewdirs, device=dev, dtype=bf)
+                  for _ in range(plan.cfg.net_depth_viewdirs)]
+      st.raw_rgb = torch.empty(B, S, 3, device=dev)
+      st.d_raw_rgb = torch.empty(B, S, 3, device=dev)
+    else:
+      st.raw_rgb = None
+      st.d_raw_rgb = None
+    st.dy = None   # gradient ping-pong buffers, allocated on first backward
+    self._levels[key] = st
+    return st
+
+  # ------------------------------------------------------------------ forward
+  def _mlp_forward(self, st: LevelState, mlp: MLPDevice, rays, impl=0):
+    plan = mlp.plan
+    cfg = plan.cfg
+    B, S = st.B, st.S
+    M = B * S
+    W = cfg.net_width
+    m = self.mcfg
+    ops.encode(st.sdist, rays.origins, rays.directions, rays.radii_flat, rays.near_flat,
+               rays.far_flat, mlp.basis, min_deg=cfg.min_deg_point, max_deg=cfg.max_deg_point,
+               raydist_fn=m.raydist_fn, ray_shape=m.ray_shape, warp_contract=cfg.warp_fn == 'contract',
+               disable_integration=m.disable_integration, feat=st.feat, feat_cols=plan.Fpad)
+    for c in st.feat_copies:
+      c.copy_(st.feat)
+    x = st.feat
+    trunk = plan.by_role('trunk')
+    for i, s in enumerate(trunk):
+      out = st.acts[i][:, :W]
+      ops.gemm(L.GEMM_FWD, x, mlp.w_nk[s.name], out, m=M, n=W, k=s.in_pad, act=L.ACT_RELU,
+               bias=mlp.b(s), impl=impl)
+      x = st.acts[i]          # full width (incl. concatenated features) feeds the next layer
+    st.x_last = x
+    d = plan.by_role('density')[0]
+    ops.head_fwd(x, mlp.w_nk[d.name], mlp.b(d), 1, d.in_pad, raw=st.raw_density.view(M, 1))
+    if plan.has_rgb:
+      bt = plan.by_role('bottleneck')[0]
+      ops.gemm(L.GEMM_FWD, x, mlp.w_nk[bt.name], st.vin[:, :bt.out_dim], m=M, n=bt.out_dim,
+               k=bt.in_pad, act=L.ACT_NONE, bias=mlp.b(bt), impl=impl)
+      ops.viewdir_enc(rays.viewdirs, S, cfg.deg_view, st.vin, bt.out_dim, plan.vin_pad)
+      v = st.vin
+      for i, s in enumerate(plan.by_role('view')):
+        ops.gemm(L.GEMM_FWD, v, mlp.w_nk[s.name], st.vacts[i], m=M, n=s.out_dim, k=s.in_pad,
+                 act=L.ACT_RELU, bias=mlp.b(s), impl=impl)
+        v = st.vacts[i]
+      r = plan.by_role('rgb')[0]
+      ops.head_fwd(v, mlp.w_nk[r.name], mlp.b(r), r.out_dim, r.in_pad, raw=st.raw_rgb.view(M, 3))
+
+  def _prep_rays(self, rays):
+    r = utils.to_device_flat(rays, self.device)
+    r.radii_flat = r.radii[:, 0].contiguous()
+    r.near_flat = r.near[:, 0].contiguous()
+    r.far_flat = r.far[:, 0].contiguous()
+    return r
+
+  def forward_levels(self, rng, rays, train_frac, compute_extras, want_samples, impl=0):
+    """Runs all levels; returns the list of LevelState (buffers stay valid until the next call)."""
+    if self.params is None:
+      raise RuntimeError('Model has no parameters: call construct_model()/init() first')
+    m = self.mcfg
+    B = rays.origins.shape[0]
+    s_near, s_far, sched = self.level_schedule(train_frac)
+    dev = self.device
+    sdist_prev = torch.empty(B, 2, device=dev)
+    sdist_prev[:, 0] = s_near
+    sdist_prev[:, 1] = s_far
+    w_prev = torch.ones(B, 1, device=dev)
+    states = []
+    for i, lv in enumerate(sched):
+      mname = 'NerfMLP_0' if (m.single_mlp or not lv['is_prop']) else 'PropMLP_0'
+      mlp = self.mlps[mname]
+      st = self._level_state(i, mname, B, lv['S'])
+      st.lv = lv
+      st.is_prop = lv['is_prop']
+      jit = None
+      if rng is not None:
+        if isinstance(rng, dict):
+          jit = rng['jitter'][i].to(dev).contiguous()
+          jit = jit.reshape(B) if m.single_jitter else jit.reshape(B, lv['S'])
+        else:
+          shape = (B,) if m.single_jitter else (B, lv['S'])
+          jit = torch.rand(shape, device=dev, generator=rng)
+      u_base, max_jitter = self._u(lv['S'], jit is not None)
+      ops.sample_level(sdist_prev, w_prev, lv['S'], dilation=lv['dilation'],
+                       use_dilation=lv['use_dilation'], domain=(s_near, s_far), anneal=lv['anneal'],
+                       resample_padding=m.resample_padding, jitter=jit, single_jitter=m.single_jitter,
+                       u_base=u_base, max_jitter=max_jitter, out=st.sdist)
+      self._mlp_forward(st, mlp, rays, impl=impl)
+      st.noise = None
+      if mlp.plan.cfg.density_noise > 0 and rng is not None:
+        if isinstance(rng, dict):
+          st.noise = rng['density_noise'][i].to(dev).reshape(B, lv['S']).contiguous()
+        else:
+          st.noise = torch.randn(B, lv['S'], device=dev, generator=rng)
+      st.comp_cfg = self._comp_cfg(mlp.plan.cfg)
+      st.comp = ops.composite_fwd(st.raw_density, st.raw_rgb, st.sdist, rays.directions,
+                                  rays.near_flat, rays.far_flat, cfg=st.comp_cfg,
+                                  density_noise=st.noise, want_samples=want_samples,
+                                  want_extras=compute_extras)
+      sdist_prev, w_prev = st.sdist, st.comp['weights']
+      states.append(st)
+    return states
+
+  def __call__(self, rng, rays, train_frac, compute_extras, zero_glo=True):
+    """models.py:75-312.  rng: None (deterministic), a torch.Generator on the device, or a
+    dict of explicit draws {'jitter': [per level], 'density_noise': [per level]}."""
+    r = self._prep_rays(rays)
+    states = self.forward_levels(rng, r, train_frac, compute_extras, want_samples=True)
+    lead = tuple(np.asarray(rays.origins).shape[:-1]) if not isinstance(rays.origins, torch.Tensor) \
+        else tuple(rays.origins.shape[:-1])
+    renderings, ray_history = [], []
+    n_vis = self.config.vis_num_rays
+    for st in states:
+      c = st.comp
+      rend = {'rgb': c['rgb'].view(lead + (3,))}
+      if compute_extras:
+        rend['acc'] = c['acc'].view(lead)
+        for j, k in enumerate(['distance_mean', 'distance_percentile_5', 'distance_median',
+                               'distance_percentile_95']):
+          rend[k] = c['dist'][:, j].contiguous().view(lead)
+        rend['ray_sdist'] = st.sdist[:n_vis].clone()
+        rend['ray_weights'] = c['weights'][:n_vis].clone()
+        rend['ray_rgbs'] = c['rgb_samples'][:n_vis].clone()
+      renderings.append(rend)
+      S = st.S
+      ray_history.append(dict(
+          density=c['density'].view(lead + (S,)), rgb=c['rgb_samples'].view(lead + (S, 3)),
+          raw_grad_density=None, grad_pred=None, normals=None, normals_pred=None, roughness=None,
+          sdist=st.sdist.clone().view(lead + (S + 1,)), weights=c['weights'].view(lead + (S,))))
+    if compute_extras:
+      final_rgb = (renderings[-1]['ray_rgbs'] * renderings[-1]['ray_weights'][..., None]).sum(-2)
+      for rr in renderings[:-1]:
+        rr['ray_rgbs'] = final_rgb[:, None, :].expand(rr['ray_rgbs'].shape).contiguous()
+    return renderings, ray_history
+
+  def apply(self, variables, rng, rays, train_frac, compute_extras, zero_glo=True):
+    """flax-style entry: model.apply(variables, rng, rays, train_frac=..., compute_extras=...)."""
+    if variables is not self.params:
+      self.bind(variables)
+    return self(rng, rays, train_frac, compute_extras, zero_glo)
+
+  # ------------------------------------------------------------------ backward
+  def _mlp_backward(self, st: LevelState, mlp: MLPDevice, impl=0):
+    """Accumulates parameter gradients of one level into mlp.grads (fp32)."""
+    plan = mlp.plan
+    cfg = plan.cfg
+    M = st.B * st.S
+    W = cfg.net_width
+    dev = self.device
+    if st.dy is None:
+      st.dy = [torch.empty(M, W, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    g = mlp.grads
+    d = plan.by_role('density')[0]
+    x_last = st.x_last
+    dy = st.dy[0]
+    d_raw_density = st.d_raw_density.view(M, 1)
+    if plan.has_rgb:
+      r = plan.by_role('rgb')[0]
+      views = plan.by_role('view')
+      Wv = cfg.net_width_viewdirs
+      dv = torch.empty(M, Wv, device=dev, dtype=torch.bfloat16) if not hasattr(st, 'dv') else st.dv
+      st.dv = dv
+      v_last = st.vacts[-1]
+      ops.head_bwd(v_last, mlp.w_nk[r.name], st.d_raw_rgb.view(M, 3), r.out_dim, r.in_pad, dx=dv,
+                   relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g))
+      dcur = dv
+      for i in range(len(views) - 1, -1, -1):
+        s = views[i]
+        xin = st.vin if i == 0 else st.vacts[i - 1]
+        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(s, g), m=s.in_pad, n=s.out_dim, k=M, impl=impl)
+        ops.colsum(dcur, s.out_dim, mlp.b(s, g))
+        if i > 0:
+          nxt = torch.empty(M, Wv, device=dev, dtype=torch.bfloat16)
+          ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s.name], nxt, m=M, n=Wv, k=s.out_dim,
+                   mask=st.vacts[i - 1], impl=impl)
+          dcur = nxt
+      s0 = views[0]
+      bt = plan.by_role('bottleneck')[0]
+      if not hasattr(st, 'dbott'):
+        st.dbott = torch.empty(M, bt.out_dim, device=dev, dtype=torch.bfloat16)
+      # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
+      ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], st.dbott, m=M, n=bt.out_dim, k=s0.out_dim, impl=impl)
+      ops.gemm(L.GEMM_WGRAD, x_last, st.dbott, mlp.W(bt, g), m=bt.in_pad, n=bt.out_dim, k=M, impl=impl)
+      ops.colsum(st.dbott, bt.out_dim, mlp.b(bt, g))
+      # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
+      ops.gemm(L.GEMM_DGRAD, st.dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bt.out_dim,
+               rowv=st.d_raw_density.view(M), colv=mlp.colv_density, mask=x_last, impl=impl)
+      ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=None, dw=mlp.W(d, g),
+                   db=mlp.b(d, g))
+    else:
+      ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=dy, relu_mask=True,
+                   dw=mlp.W(d, g), db=mlp.b(d, g))
+    trunk = plan.by_role('trunk')
+    cur, other = st.dy[0], st.dy[1]
+    for i in range(len(trunk) - 1, -1, -1):
+      s = trunk[i]
+      xin = st.feat if i == 0 else st.acts[i - 1]
+      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(s, g), m=s.in_pad, n=W, k=M, impl=impl)
+      ops.colsum(cur, W, mlp.b(s, g))
+      if i > 0:
+        # only the hidden part of the input carries gradient (features are constants:
+        # stop_gradient(sdist), models.py:200-201)
+        ops.gemm(L.GEMM_DGRAD, cur, mlp.w_kn[s.name], other, m=M, n=W, k=W,
+                 mask=st.acts[i - 1][:, :W], impl=impl)
+        cur, other = other, cur
+
+
+def construct_model(rng, rays, config, device=None):
+  """models.py:315-338.  `config` is a configs.Bundle; `rng` an int seed (or None -> 0)."""
+  bundle = config if isinstance(config, configs.Bundle) else configs.Bundle(config=config)
+  model = Model(bundle, device=device)
+  seed = 0 if rng is None else (rng if isinstance(rng, int) else int(torch.as_tensor(rng).sum()))
+  variables = model.init(seed)
+  return model, variables
+
+
+def render_image(render_fn, rays, rng, config, verbose=True, world_size=1, rank=0):
+  """Render all pixels of an image in chunks (models.py:625-706).
+
+  render_fn(rng, chunk_rays) -> (renderings, ray_history) with every rank's rays gathered
+  (multinerf_b200.train_utils.create_render_fn).  `rays` leaves are [H, W, n].
+  """
+  cfg = config.config if isinstance(config, configs.Bundle) else config
+  height, width = np.asarray(rays.origins).shape[:2] if not isinstance(rays.origins, torch.Tensor) \
+      else rays.origins.shape[:2]
+  num_rays = height * width
+  flat = rays.map(lambda r: r.reshape((num_rays, -1)))
+  chunks = []
+  idx0s = range(0, num_rays, cfg.render_chunk_size)
+  for i_chunk, idx0 in enumerate(idx0s):
+    if verbose and i_chunk % max(1, len(idx0s) // 10) == 0:
+      print(f'Rendering chunk {i_chunk}/{len(idx0s)-1}')
+    chunk = flat.map(lambda r: r[idx0:idx0 + cfg.render_chunk_size])
+    actual = chunk.origins.shape[0]
+    rem = actual % world_size
+    padding = 0
+    if rem != 0:
+      padding = world_size - rem
+      def pad(r):
+        if isinstance(r, torch.Tensor):
+          return torch.cat([r, r[-1:].expand(padding, *r.shape[1:])], 0)
+        return np.concatenate([r, np.repeat(r[-1:], padding, 0)], 0)
+      chunk = chunk.map(pad)
+    per = chunk.origins.shape[0] // world_size
+    mine = chunk.map(lambda r: r[rank * per:(rank + 1) * per])
+    chunk_renderings, _ = render_fn(rng, mine)
+    if padding > 0:
+      chunk_renderings = [{k: (v[:-padding] if not k.startswith('ray_') else v) for k, v in r.items()}
+                          for r in chunk_renderings]
+    out = dict(chunk_renderings[-1])
+    for k in chunk_renderings[0]:
+      if k.startswith('ray_'):
+        out[k] = [r[k] for r in chunk_renderings]
+    chunks.append(out)
+  rendering = {}
+  for k in chunks[0]:
+    if k.startswith('ray_'):
+      rendering[k] = [torch.cat([c[k][i] for c in chunks]) for i in range(len(chunks[0][k]))]
+    else:
+      z = torch.cat([c[k] for c in chunks])
+      rendering[k] = z.reshape((height, width) + tuple(z.shape[1:]))
+  keys = [k for k in rendering if k.startswith('ray_')]
+  if keys:
+    n = rendering[keys[0]][0].shape[0]
+    # the reference takes jax.random.permutation(PRNGKey(0)) (threefry, not reproducible here):
+    # a fixed numpy permutation plays the same role
+    ray_idx = torch.as_tensor(np.random.default_rng(0).permutation(n)[:cfg.vis_num_rays])
+    for k in keys:
+      rendering[k] = [r[ray_idx.to(r.device)] for r in rendering[k]]
+  return rendering

@@ -1,0 +1,186 @@
+"""Train-step closure and render function over the CUDA hot path.
+
+Keeps the reference's surface (internal/train_utils.py):
+  setup_model(config, rng, dataset=None) -> (model, state, render_eval_pfn, train_pstep, lr_fn)
+                                                                train_utils.py:399-419
+  train_pstep(rngs, state, batch, cameras, train_frac, loss_threshold) -> (state, stats, rngs)
+                                                                train_utils.py:239-346
+  render_eval_pfn(variables, train_frac, _, rays)               train_utils.py:377-396
+The reference runs one process with `jax.pmap`; here it is one process per GPU
+(`torchrun`), rays pre-sharded per rank, and the two collectives of the path are
+NCCL: all-reduce(mean) of the flat gradient (pmean, train_utils.py:319-321) and
+all-gather of the rendered pixels (train_utils.py:380-388).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import configs
+from . import models
+from . import ops
+from . import utils
+
+
+def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1):
+  """internal/math.py:66-98 (host scalar)."""
+  if lr_init <= 0 or lr_final <= 0:
+    raise ValueError(f'Interpolants {lr_init} and {lr_final} must be positive.')
+  if lr_delay_steps > 0:
+    delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(
+        0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+  else:
+    delay_rate = 1.0
+  t = min(max(step / max_steps, 0.0), 1.0)
+  return delay_rate * math.exp(t * (math.log(lr_final) - math.log(lr_init)) + math.log(lr_init))
+
+
+def _world():
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_world_size(), dist.get_rank()
+  return 1, 0
+
+
+class TrainState:
+  """Counterpart of flax TrainState: step counter + params + Adam moments (all in `params`)."""
+
+  def __init__(self, params):
+    self.params = params
+
+  @property
+  def step(self):
+    return self.params.step
+
+
+STAT_NAMES = ('data', 'mse', 'distortion', 'interlevel')
+
+
+def create_train_step(model: models.Model, config: configs.Config, impl=0):
+  """Returns train_pstep (train_utils.py:221-346) for this rank's shard of the batch."""
+  mcfg = model.mcfg
+  if config.data_loss_type not in ('mse', 'charb', 'rawnerf'):
+    raise NotImplementedError(f'data_loss_type {config.data_loss_type!r}')
+  if config.orientation_loss_mult > 0 or config.orientation_coarse_loss_mult > 0 or \
+     config.predicted_normal_loss_mult > 0 or config.predicted_normal_coarse_loss_mult > 0:
+    raise NotImplementedError('orientation / predicted-normal losses (Ref-NeRF) are a later milestone')
+  if config.weight_decay_mults:
+    raise NotImplementedError('weight_decay_mults')
+  dev = model.device
+  stats_buf = torch.zeros(mcfg.num_levels, 8, device=dev)
+  scratch = torch.zeros(4, device=dev)
+
+  def train_step(rng, state, batch, cameras, train_frac, loss_threshold=1.0):
+    world, _ = _world()
+    params = state.params
+    if model.params is not params:
+      model.bind(params)
+    rays = batch.rays if hasattr(batch.rays, 'radii_flat') else model._prep_rays(batch.rays)
+    B = rays.origins.shape[0]
+    target = torch.as_tensor(batch.rgb).to(dev, torch.float32).reshape(B, -1)[:, :3].contiguous()
+    lossmult = rays.lossmult
+    if config.disable_multiscale_loss:
+      lossmult = torch.ones_like(lossmult)
+    lm_ch = lossmult.shape[-1]
+    inv_denom = (1.0 / (lossmult.sum() * (3 if lm_ch == 1 else 1))).reshape(1)
+    params.grads.zero_()
+    stats_buf.zero_()
+    states = model.forward_levels(rng if config.randomized else None, rays, train_frac,
+                                  compute_extras=False, want_samples=False, impl=impl)
+    fine = states[-1]
+    n = len(states)
+    for i in range(n - 1, -1, -1):
+      st = states[i]
+      is_fine = i == n - 1
+      ops.composite_bwd(
+          st.raw_density, st.raw_rgb, st.sdist, rays.directions, rays.near_flat, rays.far_flat,
+          target, lossmult, inv_denom, stats_buf[i], cfg=st.comp_cfg,
+          loss_type=config.data_loss_type, charb_padding=config.charb_padding,
+          data_mult=config.data_loss_mult if is_fine else config.data_coarse_loss_mult,
+          distortion_mult=config.distortion_loss_mult if is_fine else 0.0,
+          interlevel_mult=0.0 if is_fine else config.interlevel_loss_mult,
+          sdist_fine=None if is_fine else fine.sdist,
+          weights_fine=None if is_fine else fine.comp['weights'],
+          density_noise=st.noise, d_raw_density=st.d_raw_density, d_raw_rgb=st.d_raw_rgb)
+      model._mlp_backward(st, model.mlps[st.mname], impl=impl)
+    if world > 1:
+      dist.all_reduce(params.grads, op=dist.ReduceOp.SUM)
+      dist.all_reduce(stats_buf, op=dist.ReduceOp.SUM)
+      stats_buf.div_(world)
+    params.step += 1
+    lr = learning_rate_decay(params.step - 1, config.lr_init, config.lr_final, config.max_steps,
+                             config.lr_delay_steps, config.lr_delay_mult)
+    for name in model.plans:
+      ops.clip_adam(params.seg(name), params.seg(name, params.grads), params.seg(name, params.mu),
+                    params.seg(name, params.nu), scratch, step=params.step, lr=lr,
+                    beta1=config.adam_beta1, beta2=config.adam_beta2, eps=config.adam_eps,
+                    grad_max_val=config.grad_max_val, grad_max_norm=config.grad_max_norm,
+                    grad_scale=1.0 / world)
+    for mlp in model.mlps.values():
+      mlp.repack()
+    stats = LazyStats(stats_buf, n)
+    return state, stats, rng
+
+  return train_step
+
+
+class LazyStats(dict):
+  """Reads the device-side loss accumulators only when asked (no sync in the step)."""
+
+  def __init__(self, buf, n):
+    super().__init__()
+    self._buf, self._n = buf, n
+
+  def materialize(self):
+    b = self._buf.detach().cpu()
+    mses = b[:, 1].clone()
+    losses = {'data': float(b[:, 0].sum()), 'interlevel': float(b[:, 3].sum()),
+              'distortion': float(b[:, 2].sum())}
+    self.update(mses=mses, psnrs=-10.0 / math.log(10.0) * torch.log(mses), losses=losses,
+                loss=sum(losses.values()))
+    self['psnr'] = float(self['psnrs'][-1])
+    return self
+
+
+def create_render_fn(model: models.Model):
+  """render_eval_pfn(variables, train_frac, _, rays): deterministic render of this rank's rays,
+  with the per-rank pixel buffers all-gathered (train_utils.py:377-396)."""
+
+  def render_eval_fn(variables, train_frac, _, rays):
+    world, rank = _world()
+    renderings, ray_history = model.apply(variables, None, rays, train_frac=train_frac,
+                                          compute_extras=True)
+    if world > 1:
+      out = []
+      for r in renderings:
+        g = {}
+        for k, v in r.items():
+          if k.startswith('ray_'):
+            g[k] = v
+            continue
+          v = v.contiguous()
+          buf = torch.empty((world,) + tuple(v.shape), device=v.device, dtype=v.dtype)
+          dist.all_gather_into_tensor(buf, v)
+          g[k] = buf.reshape((-1,) + tuple(v.shape[1:]))
+        out.append(g)
+      renderings = out
+    return renderings, ray_history
+
+  return render_eval_fn
+
+
+def create_optimizer(config, variables):
+  lr_fn = lambda step: learning_rate_decay(step, config.lr_init, config.lr_final, config.max_steps,
+                                           config.lr_delay_steps, config.lr_delay_mult)
+  return TrainState(variables), lr_fn
+
+
+def setup_model(config, rng, dataset=None, device=None):
+  """train_utils.py:399-419.  `config` is a configs.Bundle (Config + Model + MLP bindings)."""
+  bundle = config if isinstance(config, configs.Bundle) else configs.Bundle(config=config)
+  dummy = utils.dummy_rays(include_exposure_idx=bundle.config.rawnerf_mode,
+                           include_exposure_values=True)
+  model, variables = models.construct_model(rng, dummy, bundle, device=device)
+  state, lr_fn = create_optimizer(bundle.config, variables)
+  render_eval_pfn = create_render_fn(model)
+  train_pstep = create_train_step(model, bundle.config)
+  return model, state, render_eval_pfn, train_pstep, lr_fn

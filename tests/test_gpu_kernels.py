@@ -330,12 +330,12 @@ def test_heads_and_colsum(ops):
     close(raw, x.float() @ w.float().T + b, atol=1e-4, rtol=1e-4, msg='head fwd')
     draw = torch.tensor(rng.normal(size=(M, n_out)).astype(np.float32))
     dx = torch.empty(M, K, dtype=torch.bfloat16, device='cuda')
-    dw = torch.zeros(n_out, K, device='cuda')
+    dw = torch.zeros(K, n_out, device='cuda')
     db = torch.zeros(n_out, device='cuda')
     ops.head_bwd(x.cuda(), w.cuda(), draw.cuda(), n_out, K, dx=dx, relu_mask=True, dw=dw, db=db)
     ref_dx = (draw @ w.float()) * (x.float() > 0)
     close(dx.float(), ref_dx.to(torch.bfloat16).float(), atol=1e-2, rtol=1e-2, msg='head dx')
-    close(dw, draw.T @ x.float(), atol=2e-3, rtol=1e-4, msg='head dw')
+    close(dw, x.float().T @ draw, atol=2e-3, rtol=1e-4, msg='head dw')
     close(db, draw.sum(0), atol=1e-3, rtol=1e-4, msg='head db')
   x = _bf(rng.normal(size=(5000, 256)).astype(np.float32))
   out = torch.zeros(256, device='cuda')

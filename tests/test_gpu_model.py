@@ -1,0 +1,192 @@
+"""Model-level parity on the GPU: Model.__call__ and the train step vs the CPU oracle on
+identical synthetic rays and weights.  Needs a B200.
+
+The Dense layers run in bf16 on tensor cores, so the oracle is evaluated with the same
+bf16-rounded weights and bf16-rounded layer inputs (fp32 accumulation) -- see
+oracle/o_models.py `bf16=True`.  Achieved errors are asserted with explicit tolerances.
+"""
+import copy
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import o_models, o_train
+from util import close
+
+pytestmark = pytest.mark.gpu
+
+
+def synth_rays(seed, B, near, far, unit_cube=True, radius=4.0):
+  from multinerf_b200 import utils
+  rng = np.random.default_rng(seed)
+  if unit_cube:
+    o = rng.uniform(-1, 1, (B, 3))
+    d = rng.normal(size=(B, 3))
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+  else:   # cameras on a sphere looking at the origin (tests/render_test.py:137-143 style)
+    o = rng.normal(size=(B, 3))
+    o = o / np.linalg.norm(o, axis=-1, keepdims=True) * radius
+    d = -o / radius + rng.normal(size=(B, 3)) * 0.1
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+  v = d.copy()
+  d = d * rng.uniform(0.8, 1.2, (B, 1))
+  f = np.float32
+  return utils.Rays(origins=o.astype(f), directions=d.astype(f), viewdirs=v.astype(f),
+                    radii=rng.uniform(5e-4, 1e-3, (B, 1)).astype(f),
+                    imageplane=np.zeros((B, 2), f), lossmult=np.ones((B, 1), f),
+                    near=np.full((B, 1), near, f), far=np.full((B, 1), far, f),
+                    cam_idx=np.zeros((B, 1), np.int32)), rng
+
+
+def mini360():
+  from multinerf_b200 import configs
+  b = configs.bundle_360()
+  b.model.num_prop_samples = 32
+  b.model.num_nerf_samples = 16
+  b.prop_mlp.net_depth, b.prop_mlp.net_width = 2, 64
+  b.nerf_mlp.net_depth, b.nerf_mlp.net_width = 6, 128
+  b.nerf_mlp.bottleneck_width, b.nerf_mlp.net_width_viewdirs = 64, 64
+  return b
+
+
+def plumbing_blender():
+  from multinerf_b200 import configs
+  b = configs.bundle_blender_256()
+  b.model.num_levels = 1
+  b.model.num_nerf_samples = 32
+  return b
+
+
+def torch_tree(tree):
+  return {k: (torch_tree(v) if isinstance(v, dict) else torch.tensor(v)) for k, v in tree.items()}
+
+
+class TRays:
+  pass
+
+
+def oracle_rays(rays):
+  r = TRays()
+  for k, v in rays.__dict__.items():
+    setattr(r, k, None if v is None else torch.tensor(np.asarray(v)))
+  return r
+
+
+@pytest.fixture(scope='module')
+def mods():
+  from multinerf_b200 import lib, models, train_utils
+  lib.require_device()
+  return models, train_utils
+
+
+def test_param_counts_known_answers(mods):
+  # scripts/generate_tables.ipynb:145 and sibling rows
+  from multinerf_b200 import configs
+  models, _ = mods
+  assert models.Model(configs.bundle_360()).num_params() == 9007493
+  assert models.Model(configs.bundle_blender_256()).num_params() == 835205
+
+
+@pytest.mark.parametrize('which', ['plumbing', 'mini360'])
+def test_model_forward_vs_oracle(mods, which):
+  models, _ = mods
+  bundle = plumbing_blender() if which == 'plumbing' else mini360()
+  B = 64 if which == 'plumbing' else 160
+  near, far = (2.0, 6.0) if which == 'plumbing' else (0.2, 1e6)
+  rays, rng = synth_rays(0 if which == 'plumbing' else 1, B, near, far, unit_cube=which != 'plumbing')
+  model, variables = models.construct_model(2, rays, bundle)
+  params = torch_tree(model.export_flax())
+  bases = {'nerf': model.plans['NerfMLP_0'].basis,
+           'prop': model.plans.get('PropMLP_0', model.plans['NerfMLP_0']).basis}
+  orays = oracle_rays(rays)
+  sched = model.level_schedule(0.5)[2]
+  for randomized in [False, True]:
+    rand = None
+    if randomized:
+      rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, 1)).astype(np.float32)) for _ in sched]}
+    with torch.no_grad():
+      rend_o, hist_o, dbg_o = o_models.model_apply(params, bundle, bases, orays, 0.5, True, rand=rand,
+                                                   bf16=True, return_debug=True)
+    rend, hist = model(rand, rays, 0.5, True)
+    torch.cuda.synchronize()
+    # level 0 resamples the trivial [0,1] histogram: identical inputs on both sides
+    close(hist[0]['sdist'], hist_o[0]['sdist'], atol=1e-6, rtol=1e-6, msg='level-0 sdist')
+    # per-level check with the sample positions pinned to the oracle's
+    B_, lv_states = B, model.forward_levels(rand, model._prep_rays(rays), 0.5, True, True)
+    r = model._prep_rays(rays)
+    from multinerf_b200 import ops
+    for i, st in enumerate(lv_states):
+      st.sdist.copy_(hist_o[i]['sdist'].cuda())
+      model._mlp_forward(st, model.mlps[st.mname], r)
+      comp = ops.composite_fwd(st.raw_density, st.raw_rgb, st.sdist, r.directions, r.near_flat, r.far_flat,
+                               cfg=st.comp_cfg, want_samples=True, want_extras=True)
+      torch.cuda.synchronize()
+      dens_o, dens = hist_o[i]['density'], comp['density'].cpu()
+      # bf16 tensor-core MLP vs bf16-emulating oracle: state the achieved error
+      err = (dens - dens_o).abs() / (1.0 + dens_o.abs())
+      assert float(err.max()) < 0.08 and float(err.mean()) < 4e-3, (i, float(err.max()), float(err.mean()))
+      close(comp['weights'], hist_o[i]['weights'], atol=2e-2, rtol=0, msg=f'weights level {i}')
+      close(comp['rgb'], rend_o[i]['rgb'], atol=1e-2, rtol=0, msg=f'pixel level {i}')
+      if st.raw_rgb is not None:
+        close(comp['rgb_samples'], hist_o[i]['rgb'], atol=3e-2, rtol=0, msg=f'rgb samples level {i}')
+      close(comp['acc'], rend_o[i]['acc'], atol=1e-2, rtol=0, msg=f'acc level {i}')
+    # end to end (sample positions drift with the bf16-level differences of earlier levels)
+    close(rend[-1]['rgb'], rend_o[-1]['rgb'], atol=2e-2, rtol=0, msg='final pixel end-to-end')
+    assert rend[-1]['rgb'].shape == (B, 3) and hist[-1]['weights'].shape == (B, sched[-1]['S'])
+    for k in ['acc', 'distance_mean', 'distance_median', 'distance_percentile_5', 'distance_percentile_95',
+              'ray_sdist', 'ray_weights', 'ray_rgbs']:
+      assert k in rend[-1]
+
+
+@pytest.mark.parametrize('which,impl', [('mini360', 1), ('mini360', 0), ('plumbing', 0)])
+def test_train_step_vs_oracle(mods, which, impl):
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  bundle = plumbing_blender() if which == 'plumbing' else mini360()
+  bundle.config.grad_max_norm = 0.0      # compare raw Adam first; clipping is covered below
+  B = 64 if which == 'plumbing' else 160
+  near, far = (2.0, 6.0) if which == 'plumbing' else (0.2, 1e6)
+  rays, rng = synth_rays(3, B, near, far, unit_cube=which != 'plumbing')
+  target = rng.uniform(0, 1, (B, 3)).astype(np.float32)
+  model, variables = models.construct_model(4, rays, bundle)
+  params0 = torch_tree(model.export_flax())
+  bases = {'nerf': model.plans['NerfMLP_0'].basis,
+           'prop': model.plans.get('PropMLP_0', model.plans['NerfMLP_0']).basis}
+  sched = model.level_schedule(0.5)[2]
+  rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, 1)).astype(np.float32)) for _ in sched]}
+  # oracle step (bf16-emulated forward, fp32 autograd)
+  opt0 = {'count': 0, 'mu': {}, 'nu': {}}
+  new_o, opt_o, stats_o, grads_o = o_train.train_step(params0, opt0, bundle, bases, oracle_rays(rays),
+                                                      torch.tensor(target), 0.5, rand=rand, bf16=True)
+  step_fn = train_utils.create_train_step(model, bundle.config, impl=impl)
+  state = train_utils.TrainState(variables)
+  batch = utils.Batch(rays=rays, rgb=target)
+  state, stats, _ = step_fn(rand, state, batch, None, 0.5)
+  torch.cuda.synchronize()
+  stats.materialize()
+  close(stats['mses'], stats_o['mses'].detach(), atol=2e-3, rtol=2e-2, msg='mses')
+  assert abs(stats['loss'] - float(stats_o['loss'])) < 2e-2 * max(1.0, abs(float(stats_o['loss'])))
+  g = model.export_grads_flax()
+  worst = 0.0
+  for mname in g:
+    for lname in g[mname]:
+      for leaf in ['kernel', 'bias']:
+        a = torch.tensor(g[mname][lname][leaf]).double().flatten()
+        b = grads_o[(mname, lname, leaf)].double().flatten()
+        denom = b.norm().clamp(min=1e-12)
+        rel = float((a - b).norm() / denom)
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+        worst = max(worst, rel)
+        assert rel < 0.08 and cos > 0.995, (mname, lname, leaf, rel, cos)
+  # parameters after one Adam step (first step moves every weight by ~lr regardless of scale)
+  newp = model.export_flax()
+  lr = o_train.lr_at(0, bundle.config)
+  for mname in newp:
+    for lname in newp[mname]:
+      a = torch.tensor(newp[mname][lname]['kernel'])
+      b = new_o[mname][lname]['kernel']
+      assert float((a - b).abs().max()) <= 2.1 * lr, (mname, lname)
+      agree = ((a - params0[mname][lname]['kernel']).sign() == (b - params0[mname][lname]['kernel']).sign())
+      assert float(agree.float().mean()) > 0.97, (mname, lname, float(agree.float().mean()))

@@ -19,6 +19,7 @@ def close(a, b, atol=1e-5, rtol=1e-5, msg=''):
   a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
   b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
   assert a.shape == b.shape, (msg, a.shape, b.shape)
+  a, b = np.atleast_1d(a), np.atleast_1d(b)
   both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
   both_nan = np.isnan(a) & np.isnan(b)
   err = np.abs(a - b)
