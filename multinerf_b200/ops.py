@@ -13,6 +13,16 @@ from . import lib as L
 
 EPS = float(torch.finfo(torch.float32).eps)
 
+# Instrumentation used by bench.py: number of kernels launched (counted per ABI call), and --
+# when set to a list -- CUDA event pairs around every tensor-core GEMM launch.
+LAUNCHES = 0
+GEMM_EVENTS = None
+
+
+def _count(n=1):
+  global LAUNCHES
+  LAUNCHES += n
+
 
 def _f32(t):
   assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), 'need contiguous fp32'
@@ -54,6 +64,7 @@ def sample_level(sdist_prev, w_prev, num_samples, *, dilation=0.0, use_dilation=
   cw = torch.empty(B, nb + 1, device=dev) if want_debug else None
   tdil = torch.empty(B, nb + 1, device=dev) if want_debug else None
   wdil = torch.empty(B, nb, device=dev) if want_debug else None
+  _count()
   L.check(lib.mnrf_sample_level(C.byref(d), L.ptr(_f32(sdist_prev)), L.ptr(_f32(w_prev)),
                                 L.ptr(_f32(u_base)), L.ptr(_f32(jitter)), L.ptr(_f32(cw_in)),
                                 L.ptr(sdist), L.ptr(idx), L.ptr(cw), L.ptr(tdil), L.ptr(wdil),
@@ -84,6 +95,7 @@ def encode(sdist, origins, directions, radii, near, far, basis, *, min_deg, max_
                    int(disable_integration), K, min_deg, max_deg, ld, feat_cols)
   f32 = torch.empty(B * S, F, device=sdist.device) if want_f32 else None
   tdist = torch.empty(B, S + 1, device=sdist.device) if want_tdist else None
+  _count()
   L.check(lib.mnrf_encode(C.byref(d), L.ptr(_f32(sdist)), L.ptr(_f32(origins)),
                           L.ptr(_f32(directions)), L.ptr(_f32(radii)), L.ptr(_f32(near)),
                           L.ptr(_f32(far)), L.ptr(_f32(basis)), L.ptr(feat), L.ptr(f32),
@@ -94,6 +106,7 @@ def encode(sdist, origins, directions, radii, near, far, basis, *, min_deg, max_
 def viewdir_enc(viewdirs, num_samples, deg, out, col0, col_end):
   lib = L.load()
   B = viewdirs.shape[0]
+  _count()
   L.check(lib.mnrf_viewdir_enc(B, num_samples, deg, L.ptr(_f32(viewdirs)), L.ptr(out),
                                out.stride(0), col0, col_end, L.stream_ptr()))
 
@@ -106,8 +119,16 @@ def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv
     assert t.stride(-1) == 1
   d = L.GemmDesc(mode, act, m, n, k, a.stride(0), b.stride(0), out.stride(0),
                  mask.stride(0) if mask is not None else 0, impl)
+  _count()
+  ev = None
+  if GEMM_EVENTS is not None:
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[0].record()
   L.check(lib.mnrf_gemm(C.byref(d), L.ptr(a), L.ptr(b), L.ptr(bias), L.ptr(rowv), L.ptr(colv),
                         L.ptr(mask), L.ptr(out), L.stream_ptr()))
+  if ev is not None:
+    ev[1].record()
+    GEMM_EVENTS.append((ev[0], ev[1], 2.0 * m * n * k))
   return out
 
 
@@ -116,6 +137,7 @@ def head_fwd(x, w_nk, bias, n_out, k, raw=None):
   M = x.shape[0]
   if raw is None:
     raw = torch.empty(M, n_out, device=x.device)
+  _count()
   L.check(lib.mnrf_head_fwd(M, k, n_out, L.ptr(x), x.stride(0), L.ptr(w_nk), L.ptr(bias),
                             L.ptr(raw), L.stream_ptr()))
   return raw
@@ -124,6 +146,7 @@ def head_fwd(x, w_nk, bias, n_out, k, raw=None):
 def head_bwd(x, w_nk, draw, n_out, k, dx=None, relu_mask=False, dw=None, db=None):
   lib = L.load()
   M = x.shape[0]
+  _count()
   L.check(lib.mnrf_head_bwd(M, k, n_out, L.ptr(x), x.stride(0), L.ptr(w_nk), L.ptr(_f32(draw)),
                             L.ptr(dx), dx.stride(0) if dx is not None else 0, int(relu_mask),
                             L.ptr(dw), L.ptr(db), L.stream_ptr()))
@@ -131,6 +154,7 @@ def head_bwd(x, w_nk, draw, n_out, k, dx=None, relu_mask=False, dw=None, db=None
 
 def colsum(x, n, out):
   lib = L.load()
+  _count()
   L.check(lib.mnrf_colsum(x.shape[0], n, L.ptr(x), x.stride(0), L.ptr(out), L.stream_ptr()))
 
 
@@ -156,6 +180,7 @@ def composite_fwd(raw_density, raw_rgb, sdist, directions, near, far, *, cfg, de
   rgbs = torch.empty(B, S, 3, device=dev) if want_samples else None
   acc = torch.empty(B, device=dev) if want_extras else None
   dist = torch.empty(B, 4, device=dev) if want_extras else None
+  _count()
   L.check(lib.mnrf_composite_fwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
                                  L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
                                  L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
@@ -179,6 +204,7 @@ def composite_bwd(raw_density, raw_rgb, sdist, directions, near, far, target_rgb
     d_raw_density = torch.empty(B, S, device=dev)
   if raw_rgb is not None and d_raw_rgb is None:
     d_raw_rgb = torch.empty(B, S, 3, device=dev)
+  _count()
   L.check(lib.mnrf_composite_bwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
                                  L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
                                  L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
@@ -195,6 +221,7 @@ def clip_adam(params, grads, mu, nu, scratch, *, step, lr, beta1, beta2, eps, gr
   lib = L.load()
   d = L.AdamDesc(params.numel(), float(grad_max_val), float(grad_max_norm), float(lr), float(beta1),
                  float(beta2), float(eps), int(step), float(grad_scale))
+  _count(2 if grad_max_norm > 0 else 1)
   L.check(lib.mnrf_clip_adam(C.byref(d), L.ptr(params), L.ptr(grads), L.ptr(mu), L.ptr(nu),
                              L.ptr(scratch), L.stream_ptr()))
 
@@ -202,5 +229,6 @@ def clip_adam(params, grads, mu, nu, scratch, *, step, lr, beta1, beta2, eps, gr
 def pack_weights(master, w_nk, w_kn):
   lib = L.load()
   in_pad, out = master.shape
+  _count()
   L.check(lib.mnrf_pack_weights(in_pad, out, L.ptr(master), L.ptr(w_nk), L.ptr(w_kn),
                                 L.stream_ptr()))

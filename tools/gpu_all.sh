@@ -1,0 +1,7 @@
+#!/bin/bash
+# tests + smoke + short bench on one B200
+mkdir -p gpurun_out
+bash tools/gpu_kernel_tests.sh > /dev/null 2>&1
+tail -60 gpurun_out/kernel_tests.log
+echo "=== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5
+echo "=== bench"; timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 --cpu_rays 128 2>&1 | tail -5 | tee gpurun_out/bench.log
