@@ -238,7 +238,10 @@ def cpu_baseline(n_rays, steps, warmup):
   from multinerf_b200 import configs, geopoly
   from oracle import o_train
   cores = os.cpu_count() or 1
-  torch.set_num_threads(cores)
+  # "all the host threads it can use": torch-CPU's intra-op pool stops scaling (and degrades) past a
+  # few dozen threads on these many-small-op graphs, so use min(cores, 32) and say so.
+  threads = min(cores, int(os.environ.get('MNRF_CPU_THREADS', '32')))
+  torch.set_num_threads(threads)
   bundle = configs.bundle_360()
   rng = np.random.default_rng(2)
   bases = {}
@@ -287,7 +290,7 @@ def cpu_baseline(n_rays, steps, warmup):
     params, opt, _, _ = o_train.train_step(params, opt, bundle, bases, rays, target, 0.5, rand=rand)
     times.append(time.perf_counter() - t0)
   t = float(np.mean(times[warmup:]))
-  return {'value': n_rays / t, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+  return {'value': n_rays / t, 'unit': 'rays/s', 'cores': threads, 'host_cores': cores, 'kind': 'port',
           'sample': f'{n_rays} rays x (64+64+32) samples of the same 360.gin train step, fp32 torch-CPU, '
                     f'{steps} timed step(s) after {warmup} warm-up; CPU restatement of the reference '
                     '(JAX/Flax are not installable in this image)',
