@@ -102,10 +102,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0):
           weights_fine=None if is_fine else fine.comp['weights'],
           density_noise=st.noise, d_raw_density=st.d_raw_density, d_raw_rgb=st.d_raw_rgb)
       model._mlp_backward(st, model.mlps[st.mname], impl=impl)
-    if world > 1:
-      dist.all_reduce(params.grads, op=dist.ReduceOp.SUM)
-      dist.all_reduce(stats_buf, op=dist.ReduceOp.SUM)
-      stats_buf.div_(world)
+    grad_scale = allreduce_mean_(params.grads, stats_buf, world)
     params.step += 1
     lr = learning_rate_decay(params.step - 1, config.lr_init, config.lr_final, config.max_steps,
                              config.lr_delay_steps, config.lr_delay_mult)
@@ -114,7 +111,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0):
                     params.seg(name, params.nu), scratch, step=params.step, lr=lr,
                     beta1=config.adam_beta1, beta2=config.adam_beta2, eps=config.adam_eps,
                     grad_max_val=config.grad_max_val, grad_max_norm=config.grad_max_norm,
-                    grad_scale=1.0 / world)
+                    grad_scale=grad_scale)
     for mlp in model.mlps.values():
       mlp.repack()
     stats = LazyStats(stats_buf, n)
@@ -141,6 +138,37 @@ class LazyStats(dict):
     return self
 
 
+def gather_renderings(renderings, world):
+  """all_gather of every per-pixel buffer (lax.all_gather, train_utils.py:380-388); `ray_*`
+  visualisation bundles stay local.  Rank r's rows land at [r*n, (r+1)*n)."""
+  if world <= 1:
+    return renderings
+  out = []
+  for r in renderings:
+    g = {}
+    for k, v in r.items():
+      if k.startswith('ray_'):
+        g[k] = v
+        continue
+      v = v.contiguous()
+      buf = torch.empty((world * v.shape[0],) + tuple(v.shape[1:]), device=v.device, dtype=v.dtype)
+      dist.all_gather_into_tensor(buf, v)
+      g[k] = buf
+    out.append(g)
+  return out
+
+
+def allreduce_mean_(grads, stats, world):
+  """pmean of gradients and stats (train_utils.py:319-321): SUM all-reduce here, the 1/world
+  factor is applied to the gradient inside clip_adam (grad_scale) and to the stats in place."""
+  if world <= 1:
+    return 1.0
+  dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+  dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+  stats.div_(world)
+  return 1.0 / world
+
+
 def create_render_fn(model: models.Model):
   """render_eval_pfn(variables, train_frac, _, rays): deterministic render of this rank's rays,
   with the per-rank pixel buffers all-gathered (train_utils.py:377-396)."""
@@ -149,20 +177,7 @@ def create_render_fn(model: models.Model):
     world, rank = _world()
     renderings, ray_history = model.apply(variables, None, rays, train_frac=train_frac,
                                           compute_extras=True)
-    if world > 1:
-      out = []
-      for r in renderings:
-        g = {}
-        for k, v in r.items():
-          if k.startswith('ray_'):
-            g[k] = v
-            continue
-          v = v.contiguous()
-          buf = torch.empty((world,) + tuple(v.shape), device=v.device, dtype=v.dtype)
-          dist.all_gather_into_tensor(buf, v)
-          g[k] = buf.reshape((-1,) + tuple(v.shape[1:]))
-        out.append(g)
-      renderings = out
+    renderings = gather_renderings(renderings, world)
     return renderings, ray_history
 
   return render_eval_fn
