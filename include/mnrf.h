@@ -104,6 +104,7 @@ int mnrf_viewdir_enc(int32_t num_rays, int32_t num_samples, int32_t deg, const f
  * GEMMs, bf16 operands, fp32 accumulation in TMEM.
  *   mode FWD  : out[M,N] bf16 = act(A[M,K] * Bt[N,K]^T + bias[N])           (A, Bt K-major)
  *   mode DGRAD: out[M,N] bf16 = (A[M,K] * Bt[N,K]^T + rowv[M]*colv[N]) masked by mask[M,N]>0
+ *               (or by the 1-bit `maskbits`)
  *               (A = dY, Bt = W in [in,out] layout; mask = stored activation; all optional)
  *   mode WGRAD: out[Mo,N] fp32 += A[R,Mo]^T * B[R,N]   (A = X, B = dY, both row-major with
  *               the reduction index R on rows: "MN-major" operands), split over R, fp32 atomics
@@ -118,12 +119,16 @@ typedef struct {
   int64_t m;          /* rows of the output (FWD/DGRAD: samples; WGRAD: `in` features) */
   int32_t n, k;       /* output columns; reduction length (WGRAD: number of samples R) */
   int64_t lda, ldb, ldc, ldmask;
+  int64_t ldmaskbits; /* row pitch of `maskbits` in 32-bit words */
   int32_t impl;       /* 0 = tcgen05 (product path); 1 = SIMT reference kernel (bring-up/tests) */
 } mnrf_gemm_desc;
 
+/* maskbits (optional): 1-bit ReLU masks, word w of row m covers columns [32w, 32w+32).  FWD with
+ * MNRF_ACT_RELU writes them (bit = output > 0); DGRAD reads them instead of the bf16 `mask`
+ * (16x less mask traffic).  The caller zero-fills nothing: every word of the tile is written. */
 int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
-              const float* rowv, const float* colv, const mnrf_bf16* mask, void* out,
-              mnrf_stream stream);
+              const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
+              void* out, mnrf_stream stream);
 
 /* ---- small heads (N <= 4 outputs): density / rgb / predicted normals ---------------------
  * raw[M, n_out] = X[M, K](bf16) * W[n_out, K](bf16) + b, fp32 accumulate; models.py:460,585.

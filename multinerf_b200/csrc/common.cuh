@@ -82,6 +82,27 @@ __device__ __forceinline__ float safe_sin_f(float x) {
   return sinf(x);
 }
 
+// Same function for the bulk of the IPE features (1.3e9 evaluations per 360.gin step):
+//  * x mod fl32(100*pi) is reproduced EXACTLY without fmodf: k = floor(x/t) may be off by one, the
+//    remainder x - k*t is exact in one FMA (fmod results are representable), and the +-t fix-up is
+//    exact for the same reason;
+//  * sin of the reduced argument (|r| < 100*pi): Cody-Waite reduction by 2*pi (hi + lo, two FMAs)
+//    then MUFU.SIN (|arg| <= pi: abs error 2^-21.4).  Total abs error < 1e-6 (parity bar: 1e-5).
+__device__ __forceinline__ float safe_sin_fast(float x) {
+  const float t = 314.159271240234375f;  // fl32(100*pi)
+  if (!(fabsf(x) < t)) {
+    float k = floorf(__fmul_rn(x, 1.f / t));
+    float r = __fmaf_rn(-k, t, x);
+    if (r < 0.f) r = __fadd_rn(r, t);
+    else if (r >= t) r = __fsub_rn(r, t);
+    x = r;
+  }
+  const float q = rintf(__fmul_rn(x, 0.15915494309189535f));
+  float r = __fmaf_rn(-q, 6.2831854820251465f, x);
+  r = __fmaf_rn(q, 1.7484555e-7f, r);      // 2*pi = 6.2831854820251465 - 1.7484555e-7
+  return __sinf(r);
+}
+
 // s_to_t of coord.construct_ray_warps (coord.py:63-99) for one value.
 __device__ __forceinline__ float fwd_raydist(int fn, float x) {
   switch (fn) {

@@ -135,9 +135,9 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
         float sc = exp2f((float)(d.min_deg + l));
         float y = lm[k] * sc;
         float v = lv[k] * (sc * sc);
-        float e = expf(-0.5f * v);
-        float fs = e * safe_sin_f(y);
-        float fc = e * safe_sin_f(y + 1.57079637050628662109375f);
+        float e = __expf(-0.5f * v);
+        float fs = e * safe_sin_fast(y);
+        float fc = e * safe_sin_fast(y + 1.57079637050628662109375f);
         row[f] = __float2bfloat16(fs);
         row[KL + f] = __float2bfloat16(fc);
         if (feat_f32) {

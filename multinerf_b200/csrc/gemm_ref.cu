@@ -1,12 +1,14 @@
 // SIMT reference GEMM (bring-up / test cross-check of the tcgen05 kernel at sizes the CPU oracle
 // cannot reach) and the mnrf_gemm dispatcher.  Same contract as gemm_tc.cu, no tensor cores.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mnrf {
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
-                   const float* rowv, const float* colv, const mnrf_bf16* mask, void* out,
-                   cudaStream_t stream);
+                   const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
+                   void* out, cudaStream_t stream);
 
 __device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
@@ -14,7 +16,8 @@ __device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat1
 __global__ void gemm_ref_nt_kernel(mnrf_gemm_desc d, const __nv_bfloat16* __restrict__ a,
                                    const __nv_bfloat16* __restrict__ b, const float* __restrict__ bias,
                                    const float* __restrict__ rowv, const float* __restrict__ colv,
-                                   const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ out) {
+                                   const __nv_bfloat16* __restrict__ mask, uint32_t* __restrict__ maskbits,
+                                   __nv_bfloat16* __restrict__ out) {
   __shared__ float sa[16][17], sb[16][17];
   const int64_t m = (int64_t)blockIdx.y * 16 + threadIdx.y;
   const int n = blockIdx.x * 16 + threadIdx.x;
@@ -32,10 +35,17 @@ __global__ void gemm_ref_nt_kernel(mnrf_gemm_desc d, const __nv_bfloat16* __rest
   if (m >= d.m || n >= d.n) return;
   if (d.mode == MNRF_GEMM_FWD) {
     if (bias) acc += bias[n];
-    if (d.act == MNRF_ACT_RELU) acc = fmaxf(acc, 0.f);
+    if (d.act == MNRF_ACT_RELU) {
+      acc = fmaxf(acc, 0.f);
+      if (maskbits && acc > 0.f) atomicOr(&maskbits[m * d.ldmaskbits + (n >> 5)], 1u << (n & 31));
+    }
   } else {
     if (rowv) acc += rowv[m] * colv[n];
-    if (mask && !(ldbf(mask + m * d.ldmask + n) > 0.f)) acc = 0.f;
+    if (maskbits) {
+      if (!((maskbits[m * d.ldmaskbits + (n >> 5)] >> (n & 31)) & 1u)) acc = 0.f;
+    } else if (mask && !(ldbf(mask + m * d.ldmask + n) > 0.f)) {
+      acc = 0.f;
+    }
   }
   out[m * d.ldc + n] = __float2bfloat16(acc);
 }
@@ -65,21 +75,25 @@ __global__ void gemm_ref_tn_kernel(mnrf_gemm_desc d, const __nv_bfloat16* __rest
 }  // namespace mnrf
 
 extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
-                         const float* rowv, const float* colv, const mnrf_bf16* mask, void* out,
-                         mnrf_stream stream) {
+                         const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
+                         void* out, mnrf_stream stream) {
   using namespace mnrf;
   MNRF_CHECK(d && a && b && out, "mnrf_gemm: null pointer");
   MNRF_CHECK(d->mode >= 0 && d->mode <= 2, "mnrf_gemm: unknown mode %d", d->mode);
   MNRF_CHECK((rowv == nullptr) == (colv == nullptr), "mnrf_gemm: rowv and colv come together");
   if (d->m == 0 || d->n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, out, s);
+  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, maskbits, out, s);
   dim3 block(16, 16);
   if (d->mode != MNRF_GEMM_WGRAD) {
     dim3 grid((d->n + 15) / 16, (unsigned)((d->m + 15) / 16));
+    if (maskbits && d->mode == MNRF_GEMM_FWD && d->act == MNRF_ACT_RELU) {
+      // the reference kernel ORs bits in: clear the words of this [M, N/32] block first
+      MNRF_CUDA(cudaMemset2DAsync(maskbits, d->ldmaskbits * 4, 0, (size_t)(d->n / 32) * 4, d->m, s));
+    }
     gemm_ref_nt_kernel<<<grid, block, 0, s>>>(*d, reinterpret_cast<const __nv_bfloat16*>(a),
                                                reinterpret_cast<const __nv_bfloat16*>(b), bias, rowv, colv,
-                                               reinterpret_cast<const __nv_bfloat16*>(mask),
+                                               reinterpret_cast<const __nv_bfloat16*>(mask), maskbits,
                                                reinterpret_cast<__nv_bfloat16*>(out));
   } else {
     int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, d->k / 4096));

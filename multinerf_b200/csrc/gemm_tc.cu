@@ -15,6 +15,8 @@
 //                 out[Mo,N] += X^T dY, split over R with fp32 vector reductions.
 #include <cuda.h>
 
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -29,7 +31,10 @@ constexpr int NUM_STAGES = 4;
 constexpr int NUM_ACC = 2;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KiB
-constexpr int SMEM_BYTES = NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256;
+constexpr int OUT_STAGE_BYTES = 4 * 32 * 128;                // 4 epilogue warps x 32 rows x 128 B
+constexpr int NUM_OUT_STAGES = 2;
+constexpr int SMEM_BYTES = NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_OUT_STAGES * OUT_STAGE_BYTES +
+                           1024 /*align*/ + 256;
 constexpr int NUM_THREADS = 256;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -93,6 +98,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -164,18 +179,22 @@ struct GemmParams {
   const float* rowv;
   const float* colv;
   const __nv_bfloat16* mask;
+  uint32_t* maskbits;         // FWD+ReLU: written (1 bit per output, word = 32 columns); DGRAD: read
+  int64_t ldmaskbits;         // in 32-bit words
+  int use_tma_store;
   void* out;
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NUM_STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* smem_out = smem + NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + NUM_OUT_STAGES * OUT_STAGE_BYTES);
   uint64_t* full_bar = bars;                       // [NUM_STAGES]
   uint64_t* empty_bar = bars + NUM_STAGES;         // [NUM_STAGES]
   uint64_t* tfull_bar = bars + 2 * NUM_STAGES;     // [NUM_ACC]
@@ -190,6 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (MODE != MNRF_GEMM_WGRAD) prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -282,26 +302,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     int it = 0;
+    uint32_t out_group = 0;                 // running count of 64-column groups stored by this warp
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile % p.num_n_blocks;
       const int rest = tile / p.num_n_blocks;
       const int m_blk = rest % p.num_m_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase, 4);
-      tc_fence_after();
       const int64_t row = (int64_t)m_blk * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.m;
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N;
+      const int ncol0 = n_blk * p.block_n;
+      // per-row inputs are fetched before waiting for the accumulator
       float rv = 0.f;
-      if (MODE == MNRF_GEMM_DGRAD && p.rowv && row_ok) rv = p.rowv[row];
+      uint32_t mbits[MAX_BLOCK_N / 32];
+#pragma unroll
+      for (int w = 0; w < MAX_BLOCK_N / 32; ++w) mbits[w] = 0u;
+      if (MODE == MNRF_GEMM_DGRAD) {
+        if (p.rowv && row_ok) rv = p.rowv[row];
+        if (p.maskbits && row_ok) {
+          const uint32_t* mp = p.maskbits + row * p.ldmaskbits + (ncol0 >> 5);
+#pragma unroll
+          for (int w = 0; w < MAX_BLOCK_N / 32; ++w)
+            if (w * 32 < p.block_n) mbits[w] = mp[w];
+        }
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N;
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);
+        const int col = ncol0 + c0;
+        float4 cvec[8];
+        const bool have_cvec = (MODE == MNRF_GEMM_FWD && p.bias) || (MODE == MNRF_GEMM_DGRAD && p.rowv);
+        if (have_cvec && c0 + 32 <= p.block_n) {
+          const float4* cp = reinterpret_cast<const float4*>((MODE == MNRF_GEMM_FWD ? p.bias : p.colv) + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cvec[j] = __ldg(cp + j);
+        }
         tmem_ld_wait();
-        const int col = n_blk * p.block_n + c0;
-        if (row_ok) {
-          if (MODE == MNRF_GEMM_WGRAD) {
+        if (MODE == MNRF_GEMM_WGRAD) {
+          if (row_ok) {
             float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -309,58 +350,119 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             }
-          } else {
-            float v[32];
+          }
+          continue;
+        }
+        float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (MODE == MNRF_GEMM_FWD) {
-              if (p.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (MODE == MNRF_GEMM_FWD) {
+          if (p.bias) {
+            if (c0 + 32 <= p.block_n) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + min(col + j, p.n - 1));
-              }
-              if (p.act == MNRF_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += cvec[j].x; v[4 * j + 1] += cvec[j].y; v[4 * j + 2] += cvec[j].z; v[4 * j + 3] += cvec[j].w;
               }
             } else {
-              if (p.rowv) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += rv * __ldg(p.colv + min(col + j, p.n - 1));
-              }
-              if (p.mask) {
-                const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.ldmask + col);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  if (c0 + g * 8 < p.block_n) {
-                    uint4 mv = mp[g];
-                    uint32_t mm[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      if (!(bf16_lo(mm[e]) > 0.f)) v[g * 8 + 2 * e] = 0.f;
-                      if (!(bf16_hi(mm[e]) > 0.f)) v[g * 8 + 2 * e + 1] = 0.f;
-                    }
-                  }
-                }
-              }
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + min(col + j, p.n - 1));
             }
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col);
+          }
+          if (p.act == MNRF_ACT_RELU) {
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = fmaxf(v[j], 0.f);
+              bits |= (v[j] > 0.f ? 1u : 0u) << j;
+            }
+            mbits[c0 >> 5] = bits;
+          }
+        } else {
+          if (p.rowv) {
+            if (c0 + 32 <= p.block_n) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += rv * cvec[j].x; v[4 * j + 1] += rv * cvec[j].y;
+                v[4 * j + 2] += rv * cvec[j].z; v[4 * j + 3] += rv * cvec[j].w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += rv * __ldg(p.colv + min(col + j, p.n - 1));
+            }
+          }
+          if (p.maskbits) {
+            const uint32_t bits = mbits[c0 >> 5];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (bits >> j) & 1u ? v[j] : 0.f;
+          } else if (p.mask && row_ok) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.ldmask + col);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (c0 + g * 8 < p.block_n) {
-                uint4 o;
-                o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                dst[g] = o;
+                uint4 mv = mp[g];
+                uint32_t mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16_lo(mm[e]) > 0.f)) v[g * 8 + 2 * e] = 0.f;
+                  if (!(bf16_hi(mm[e]) > 0.f)) v[g * 8 + 2 * e + 1] = 0.f;
+                }
               }
             }
           }
         }
+        uint4 o[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          o[g].x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+          o[g].y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+          o[g].z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+          o[g].w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+        }
+        if (p.use_tma_store) {
+          // 64-column groups: two 32-column halves share one 32x128-byte swizzled staging slab
+          const int half = (c0 >> 5) & 1;
+          uint8_t* slab = smem_out + (out_group & 1) * OUT_STAGE_BYTES + q * (32 * 128);
+          if (half == 0) {
+            // the bulk store issued from this slab two groups ago must have finished reading it
+            if (lane == 0) tma_store_wait_read<NUM_OUT_STAGES - 1>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = half * 4 + g;
+            *reinterpret_cast<uint4*>(slab + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o[g];
+          }
+          if (half == 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_c, slab, ncol0 + c0 - 32, m_blk * BLOCK_M + q * 32);
+              tma_store_commit();
+            }
+            ++out_group;
+          }
+        } else if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (c0 + g * 8 < p.block_n) dst[g] = o[g];
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (MODE == MNRF_GEMM_FWD && p.act == MNRF_ACT_RELU && p.maskbits && row_ok) {
+        uint32_t* mp = p.maskbits + row * p.ldmaskbits + (ncol0 >> 5);
+        if (p.block_n == MAX_BLOCK_N) {
+          reinterpret_cast<uint4*>(mp)[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+          reinterpret_cast<uint4*>(mp)[1] = make_uint4(mbits[4], mbits[5], mbits[6], mbits[7]);
+        } else {
+#pragma unroll
+          for (int w = 0; w < MAX_BLOCK_N / 32; ++w)
+            if (w * 32 < p.block_n) mp[w] = mbits[w];
+        }
+      }
     }
+    if (p.use_tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -411,8 +513,8 @@ static int pick_block_n(int n) {
 }
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
-                   const float* rowv, const float* colv, const mnrf_bf16* mask, void* out,
-                   cudaStream_t stream) {
+                   const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
+                   void* out, cudaStream_t stream) {
   MNRF_CHECK(d->k % BLOCK_K == 0, "mnrf_gemm(tc): reduction length %d must be a multiple of %d", d->k, BLOCK_K);
   MNRF_CHECK(d->lda % 8 == 0 && d->ldb % 8 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0,
              "mnrf_gemm(tc): operands must be 16-byte aligned with ld %% 8 == 0");
@@ -429,6 +531,18 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   p.bias = bias; p.rowv = rowv; p.colv = colv;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask);
   p.out = out;
+  p.maskbits = maskbits;
+  p.ldmaskbits = d->ldmaskbits;
+  if (maskbits) {
+    MNRF_CHECK(d->mode != MNRF_GEMM_WGRAD, "mnrf_gemm(tc): maskbits make no sense for WGRAD");
+    MNRF_CHECK(d->n % 32 == 0 && p.block_n % 32 == 0 && d->ldmaskbits * 32 >= d->n,
+               "mnrf_gemm(tc): maskbits need N %% 32 == 0 and ldmaskbits >= N/32");
+    MNRF_CHECK(p.block_n != MAX_BLOCK_N || (d->ldmaskbits % 4 == 0 && ((uintptr_t)maskbits % 16) == 0),
+               "mnrf_gemm(tc): maskbits rows must be 16-byte aligned");
+  }
+  if (bias) MNRF_CHECK(((uintptr_t)bias % 16) == 0, "mnrf_gemm(tc): bias must be 16-byte aligned");
+  if (colv) MNRF_CHECK(((uintptr_t)colv % 16) == 0, "mnrf_gemm(tc): colv must be 16-byte aligned");
+  p.use_tma_store = (d->mode != MNRF_GEMM_WGRAD && p.block_n % 64 == 0) ? 1 : 0;
   const int sms = mnrf_num_sms();
   p.num_splits = 1;
   if (d->mode == MNRF_GEMM_WGRAD) {
@@ -446,10 +560,12 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
     MNRF_CHECK(d->ldc % 4 == 0 && ((uintptr_t)out % 16) == 0, "mnrf_gemm(tc): fp32 output must be 16-byte aligned");
   }
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
+  memset(&tc, 0, sizeof(tc));
   if (d->mode != MNRF_GEMM_WGRAD) {
     if (make_tmap(&ta, a, d->m, d->k, d->lda, BLOCK_K, BLOCK_M)) return 1;
     if (make_tmap(&tb, b, d->n, d->k, d->ldb, BLOCK_K, p.block_n)) return 1;
+    if (p.use_tma_store && make_tmap(&tc, out, d->m, d->n, d->ldc, 64, 32)) return 1;
   } else {
     // A = X[R, Mo], B = dY[R, N]; reduction index on rows
     if (make_tmap(&ta, a, d->k, d->m, d->lda, 64, BLOCK_K)) return 1;
@@ -465,7 +581,7 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
       MNRF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
       attr_set = true;                                                                                \
     }                                                                                                 \
-    gemm_tc_kernel<MODE_><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);                      \
+    gemm_tc_kernel<MODE_><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p);                      \
   } while (0)
   if (d->mode == MNRF_GEMM_FWD) MNRF_LAUNCH_TC(MNRF_GEMM_FWD);
   else if (d->mode == MNRF_GEMM_DGRAD) MNRF_LAUNCH_TC(MNRF_GEMM_DGRAD);

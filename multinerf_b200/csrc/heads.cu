@@ -153,8 +153,22 @@ colsum_kernel(int64_t M, int N, const __nv_bfloat16* __restrict__ x, int64_t ldx
   if (col >= N) return;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int64_t m = m0; m < m1; ++m) {
-    uint4 v = *reinterpret_cast<const uint4*>(x + m * ldx + col);
+  const __nv_bfloat16* base = x + col;
+  int64_t m = m0;
+  constexpr int U = 8;                     // independent 16-byte loads in flight per thread
+  for (; m + U <= m1; m += U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (m + u) * ldx));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) { acc[2 * p] += bf16_lo(vv[p]); acc[2 * p + 1] += bf16_hi(vv[p]); }
+    }
+  }
+  for (; m < m1; ++m) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(base + m * ldx));
     uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int p = 0; p < 4; ++p) { acc[2 * p] += bf16_lo(vv[p]); acc[2 * p + 1] += bf16_hi(vv[p]); }
@@ -286,7 +300,7 @@ extern "C" int mnrf_colsum(int64_t m, int32_t n, const mnrf_bf16* x, int64_t ldx
   const int threads = 128;
   dim3 grid;
   grid.y = (n / 8 + threads - 1) / threads;
-  int bx = std::max(1, mnrf_num_sms() * 8 / (int)grid.y);
+  int bx = std::max(1, mnrf_num_sms() * 16 / (int)grid.y);
   bx = (int)std::min<int64_t>(bx, (m + 63) / 64);
   grid.x = bx;
   int64_t rpb = (m + bx - 1) / bx;

@@ -34,7 +34,7 @@ class EncodeDesc(C.Structure):
 class GemmDesc(C.Structure):
   _fields_ = [('mode', C.c_int32), ('act', C.c_int32), ('m', C.c_int64), ('n', C.c_int32),
               ('k', C.c_int32), ('lda', C.c_int64), ('ldb', C.c_int64), ('ldc', C.c_int64),
-              ('ldmask', C.c_int64), ('impl', C.c_int32)]
+              ('ldmask', C.c_int64), ('ldmaskbits', C.c_int64), ('impl', C.c_int32)]
 
 
 class CompositeDesc(C.Structure):
@@ -75,7 +75,7 @@ _SIGNATURES = {
     'mnrf_encode': (C.c_int, [C.POINTER(EncodeDesc)] + [_P] * 11),
     'mnrf_viewdir_enc': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),
-    'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 8),
+    'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 9),
     'mnrf_head_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P, _P]),
     'mnrf_head_bwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P,
                                 C.c_int64, C.c_int32, _P, _P, _P]),

@@ -363,10 +363,11 @@ class Model:
     st.sdist = torch.empty(B, S + 1, device=dev)
     # trunk activations; the layer whose output is concatenated with the features owns the
     # feature columns (encode writes there), otherwise features get their own buffer
-    st.acts = []
+    st.acts, st.bits = [], []       # bf16 activations + 1-bit ReLU masks (32 columns per word)
     for i in range(plan.cfg.net_depth):
       width = W + plan.Fpad if i in plan.concat_after else W
       st.acts.append(torch.empty(M, width, device=dev, dtype=bf))
+      st.bits.append(torch.empty(M, W // 32, device=dev, dtype=torch.int32))
     if plan.concat_after:
       st.feat = st.acts[plan.concat_after[0]][:, W:]
       st.feat_copies = [st.acts[i][:, W:] for i in plan.concat_after[1:]]
@@ -378,6 +379,8 @@ class Model:
     if plan.has_rgb:
       st.vin = torch.empty(M, plan.vin_pad, device=dev, dtype=bf)
       st.vacts = [torch.empty(M, plan.cfg.net_width_viewdirs, device=dev, dtype=bf)
+                  for _ in range(plan.cfg.net_depth_viewdirs)]
+      st.vbits = [torch.empty(M, plan.cfg.net_width_viewdirs // 32, device=dev, dtype=torch.int32)
                   for _ in range(plan.cfg.net_depth_viewdirs)]
       st.raw_rgb = torch.empty(B, S, 3, device=dev)
       st.d_raw_rgb = torch.empty(B, S, 3, device=dev)
@@ -407,7 +410,7 @@ class Model:
     for i, s in enumerate(trunk):
       out = st.acts[i][:, :W]
       ops.gemm(L.GEMM_FWD, x, mlp.w_nk[s.name], out, m=M, n=W, k=s.in_pad, act=L.ACT_RELU,
-               bias=mlp.b(s), impl=impl)
+               bias=mlp.b(s), maskbits=st.bits[i], impl=impl)
       x = st.acts[i]          # full width (incl. concatenated features) feeds the next layer
     st.x_last = x
     d = plan.by_role('density')[0]
@@ -420,7 +423,7 @@ class Model:
       v = st.vin
       for i, s in enumerate(plan.by_role('view')):
         ops.gemm(L.GEMM_FWD, v, mlp.w_nk[s.name], st.vacts[i], m=M, n=s.out_dim, k=s.in_pad,
-                 act=L.ACT_RELU, bias=mlp.b(s), impl=impl)
+                 act=L.ACT_RELU, bias=mlp.b(s), maskbits=st.vbits[i], impl=impl)
         v = st.vacts[i]
       r = plan.by_role('rgb')[0]
       ops.head_fwd(v, mlp.w_nk[r.name], mlp.b(r), r.out_dim, r.in_pad, raw=st.raw_rgb.view(M, 3))
@@ -551,7 +554,7 @@ class Model:
         if i > 0:
           nxt = torch.empty(M, Wv, device=dev, dtype=torch.bfloat16)
           ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s.name], nxt, m=M, n=Wv, k=s.out_dim,
-                   mask=st.vacts[i - 1], impl=impl)
+                   maskbits=st.vbits[i - 1], impl=impl)
           dcur = nxt
       s0 = views[0]
       bt = plan.by_role('bottleneck')[0]
@@ -563,7 +566,7 @@ class Model:
       ops.colsum(st.dbott, bt.out_dim, mlp.b(bt, g))
       # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
       ops.gemm(L.GEMM_DGRAD, st.dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bt.out_dim,
-               rowv=st.d_raw_density.view(M), colv=mlp.colv_density, mask=x_last, impl=impl)
+               rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1], impl=impl)
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=None, dw=mlp.W(d, g),
                    db=mlp.b(d, g))
     else:
@@ -580,7 +583,7 @@ class Model:
         # only the hidden part of the input carries gradient (features are constants:
         # stop_gradient(sdist), models.py:200-201)
         ops.gemm(L.GEMM_DGRAD, cur, mlp.w_kn[s.name], other, m=M, n=W, k=W,
-                 mask=st.acts[i - 1][:, :W], impl=impl)
+                 maskbits=st.bits[i - 1], impl=impl)
         cur, other = other, cur
 
 

@@ -295,10 +295,19 @@ def test_gemm_fwd(ops, impl, M, N, K):
   bias = torch.tensor(rng.normal(size=(N,)).astype(np.float32))
   ref = torch.relu(a.float() @ w.float().T + bias)
   out = torch.full((M, N + 64), -3.0, dtype=torch.bfloat16, device='cuda')   # strided output view
-  ops.gemm(L.GEMM_FWD, a.cuda(), w.cuda(), out[:, :N], m=M, n=N, k=K, act=L.ACT_RELU, bias=bias.cuda(), impl=impl)
+  bits = torch.full((M, N // 32), -1, dtype=torch.int32, device='cuda')
+  ops.gemm(L.GEMM_FWD, a.cuda(), w.cuda(), out[:, :N], m=M, n=N, k=K, act=L.ACT_RELU, bias=bias.cuda(),
+           maskbits=bits, impl=impl)
   torch.cuda.synchronize()
   close(out[:, :N].float(), ref.to(torch.bfloat16).float(), atol=2e-2, rtol=1.6e-2, msg=f'fwd impl={impl}')
   assert (out[:, N:] == -3).all()
+  # 1-bit ReLU mask == (stored activation > 0), bit j of word w <-> column 32w + j
+  got = ((bits.cpu().long()[:, :, None] >> torch.arange(32)) & 1).reshape(M, N).bool()
+  assert torch.equal(got, out[:, :N].float().cpu() > 0)
+  # no activation, no bias, no mask output
+  out2 = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+  ops.gemm(L.GEMM_FWD, a.cuda(), w.cuda(), out2, m=M, n=N, k=K, impl=impl)
+  close(out2.float(), (a.float() @ w.float().T).to(torch.bfloat16).float(), atol=2e-2, rtol=1.6e-2, msg='fwd plain')
 
 
 @pytest.mark.parametrize('impl', [1, 0])
@@ -317,6 +326,18 @@ def test_gemm_dgrad(ops, impl, M, N, K):
            mask=mask.cuda(), impl=impl)
   torch.cuda.synchronize()
   close(out.float(), ref.to(torch.bfloat16).float(), atol=3e-2, rtol=1.6e-2, msg=f'dgrad impl={impl}')
+  # same mask as packed bits
+  mb = (mask.float() > 0).reshape(M, N // 32, 32).long()
+  words = (mb << torch.arange(32)).sum(-1)
+  words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+  out2 = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+  ops.gemm(L.GEMM_DGRAD, dy.cuda(), w_kn.cuda(), out2, m=M, n=N, k=K, rowv=rowv.cuda(), colv=colv.cuda(),
+           maskbits=words.cuda(), impl=impl)
+  torch.cuda.synchronize()
+  close(out2.float(), ref.to(torch.bfloat16).float(), atol=3e-2, rtol=1.6e-2, msg=f'dgrad bits impl={impl}')
+  out3 = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+  ops.gemm(L.GEMM_DGRAD, dy.cuda(), w_kn.cuda(), out3, m=M, n=N, k=K, impl=impl)
+  close(out3.float(), (dy.float() @ w_kn.float().T).to(torch.bfloat16).float(), atol=3e-2, rtol=1.6e-2, msg='dgrad plain')
 
 
 @pytest.mark.parametrize('impl', [1, 0])
