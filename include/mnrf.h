@@ -125,10 +125,12 @@ typedef struct {
 
 /* maskbits (optional): 1-bit ReLU masks, word w of row m covers columns [32w, 32w+32).  FWD with
  * MNRF_ACT_RELU writes them (bit = output > 0); DGRAD reads them instead of the bf16 `mask`
- * (16x less mask traffic).  The caller zero-fills nothing: every word of the tile is written. */
+ * (16x less mask traffic).  The caller zero-fills nothing: every word of the tile is written.
+ * bias_grad (optional, WGRAD only): db[N] += column sums of B (= dY), computed from the B tiles
+ * already staged in shared memory -- no separate pass over dY. */
 int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
               const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-              void* out, mnrf_stream stream);
+              float* bias_grad, void* out, mnrf_stream stream);
 
 /* ---- small heads (N <= 4 outputs): density / rgb / predicted normals ---------------------
  * raw[M, n_out] = X[M, K](bf16) * W[n_out, K](bf16) + b, fp32 accumulate; models.py:460,585.

@@ -78,8 +78,10 @@ __device__ __forceinline__ void contract_gauss(Gauss& g) {
   for (int i = 0; i < 3; ++i) g.mean[i] = scale * x[i];
 }
 
-// smem per warp: tdist[S+1] floats | lift_mean[K] | lift_var[K] | basis[3K] (block-shared) |
-//                row[feat_cols] bf16
+// smem: basis[3K] (block) | per warp: tdist[S+1] | gauss[S][13] | lift_mean[K] | lift_var[K] |
+//       row[feat_cols] bf16
+constexpr int kGaussStride = 13;   // 12 floats (mean 3 + cov 9), padded against bank conflicts
+
 __global__ void __launch_bounds__(256)
 encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
               const float* __restrict__ origins, const float* __restrict__ directions,
@@ -92,10 +94,11 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
   const int S = d.num_samples, K = d.basis_k, L = d.max_deg - d.min_deg, KL = K * L;
   float* sb = reinterpret_cast<float*>(smem_raw);                 // basis [K][3]
   const int row_bytes = ((d.feat_cols * 2 + 15) / 16) * 16;
-  const int per_warp_f = (S + 1) + 2 * K;
+  const int per_warp_f = (S + 1) + S * kGaussStride + 2 * K;
   float* wbase = sb + 3 * K + (size_t)wib * per_warp_f;
   float* tds = wbase;
-  float* lm = tds + (S + 1);
+  float* gs = tds + (S + 1);
+  float* lm = gs + S * kGaussStride;
   float* lv = lm + K;
   unsigned char* rows = smem_raw + (((size_t)(3 * K + nw * per_warp_f) * 4 + 15) / 16) * 16;
   __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(rows + (size_t)wib * row_bytes);
@@ -103,6 +106,9 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
   for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) sb[i] = basis[i];
   __syncthreads();
   for (int i = lane; i < d.feat_cols; i += 32) row[i] = __float2bfloat16(0.f);
+  // (l, k) of feature f = l*K + k advance by 32 features per iteration without integer division
+  const int q32 = 32 / K, r32 = 32 - q32 * K;
+  const int l_first = lane / K, k_first = lane - l_first * K;
 
   for (int ray = blockIdx.x * nw + wib; ray < d.num_rays; ray += gridDim.x * nw) {
     const float o[3] = {origins[ray * 3 + 0], origins[ray * 3 + 1], origins[ray * 3 + 2]};
@@ -116,23 +122,35 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
       if (tdist_out) tdist_out[(size_t)ray * (S + 1) + i] = t;
     }
     __syncwarp();
-    for (int s = 0; s < S; ++s) {
+    // phase A: one lane per sample -- Gaussian of the frustum, contracted
+    for (int s = lane; s < S; s += 32) {
       Gauss g;
       cast_one(d.ray_shape, tds[s], tds[s + 1], o, dv, radius, g);
       if (d.warp_contract) contract_gauss(g);
+      float* gp = gs + s * kGaussStride;
+      gp[0] = g.mean[0]; gp[1] = g.mean[1]; gp[2] = g.mean[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gp[3 + i * 3 + j] = g.cov[i][j];
+    }
+    __syncwarp();
+    // phase B: per sample, lift onto the basis and emit the 2*K*L features
+    for (int s = 0; s < S; ++s) {
+      const float* gp = gs + s * kGaussStride;
       for (int k = lane; k < K; k += 32) {
         float b0 = sb[k * 3 + 0], b1 = sb[k * 3 + 1], b2 = sb[k * 3 + 2];
-        lm[k] = g.mean[0] * b0 + g.mean[1] * b1 + g.mean[2] * b2;
-        float c0 = g.cov[0][0] * b0 + g.cov[0][1] * b1 + g.cov[0][2] * b2;
-        float c1 = g.cov[1][0] * b0 + g.cov[1][1] * b1 + g.cov[1][2] * b2;
-        float c2 = g.cov[2][0] * b0 + g.cov[2][1] * b1 + g.cov[2][2] * b2;
+        lm[k] = gp[0] * b0 + gp[1] * b1 + gp[2] * b2;
+        float c0 = gp[3] * b0 + gp[4] * b1 + gp[5] * b2;
+        float c1 = gp[6] * b0 + gp[7] * b1 + gp[8] * b2;
+        float c2 = gp[9] * b0 + gp[10] * b1 + gp[11] * b2;
         lv[k] = d.disable_integration ? 0.f : (b0 * c0 + b1 * c1 + b2 * c2);
       }
       __syncwarp();
       const size_t m = (size_t)ray * S + s;
+      int l = l_first, k = k_first;
       for (int f = lane; f < KL; f += 32) {
-        int l = f / K, k = f - l * K;
-        float sc = exp2f((float)(d.min_deg + l));
+        const float sc = __int_as_float((127 + d.min_deg + l) << 23);       // 2^(min_deg + l)
         float y = lm[k] * sc;
         float v = lv[k] * (sc * sc);
         float e = __expf(-0.5f * v);
@@ -144,6 +162,9 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
           feat_f32[m * (2 * KL) + f] = fs;
           feat_f32[m * (2 * KL) + KL + f] = fc;
         }
+        k += r32;
+        l += q32;
+        if (k >= K) { k -= K; l += 1; }
       }
       __syncwarp();
       const uint4* src = reinterpret_cast<const uint4*>(row);
@@ -198,7 +219,8 @@ extern "C" int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const 
   if (d->num_rays == 0) return 0;
   int nw = 8;
   const int row_bytes = ((d->feat_cols * 2 + 15) / 16) * 16;
-  size_t smem = (((size_t)(3 * d->basis_k + nw * ((d->num_samples + 1) + 2 * d->basis_k)) * 4 + 15) / 16) * 16 +
+  size_t smem = (((size_t)(3 * d->basis_k + nw * ((d->num_samples + 1) + d->num_samples * kGaussStride +
+                                                   2 * d->basis_k)) * 4 + 15) / 16) * 16 +
                 (size_t)nw * row_bytes;
   MNRF_CHECK(smem <= 200 * 1024, "mnrf_encode: shared memory %zu too large", smem);
   MNRF_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

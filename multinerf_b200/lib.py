@@ -75,7 +75,7 @@ _SIGNATURES = {
     'mnrf_encode': (C.c_int, [C.POINTER(EncodeDesc)] + [_P] * 11),
     'mnrf_viewdir_enc': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),
-    'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 9),
+    'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 10),
     'mnrf_head_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P, _P]),
     'mnrf_head_bwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P,
                                 C.c_int64, C.c_int32, _P, _P, _P]),

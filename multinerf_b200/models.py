@@ -549,8 +549,8 @@ class Model:
       for i in range(len(views) - 1, -1, -1):
         s = views[i]
         xin = st.vin if i == 0 else st.vacts[i - 1]
-        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(s, g), m=s.in_pad, n=s.out_dim, k=M, impl=impl)
-        ops.colsum(dcur, s.out_dim, mlp.b(s, g))
+        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(s, g), m=s.in_pad, n=s.out_dim, k=M,
+                 bias_grad=mlp.b(s, g), impl=impl)
         if i > 0:
           nxt = torch.empty(M, Wv, device=dev, dtype=torch.bfloat16)
           ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s.name], nxt, m=M, n=Wv, k=s.out_dim,
@@ -562,8 +562,8 @@ class Model:
         st.dbott = torch.empty(M, bt.out_dim, device=dev, dtype=torch.bfloat16)
       # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
       ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], st.dbott, m=M, n=bt.out_dim, k=s0.out_dim, impl=impl)
-      ops.gemm(L.GEMM_WGRAD, x_last, st.dbott, mlp.W(bt, g), m=bt.in_pad, n=bt.out_dim, k=M, impl=impl)
-      ops.colsum(st.dbott, bt.out_dim, mlp.b(bt, g))
+      ops.gemm(L.GEMM_WGRAD, x_last, st.dbott, mlp.W(bt, g), m=bt.in_pad, n=bt.out_dim, k=M,
+               bias_grad=mlp.b(bt, g), impl=impl)
       # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
       ops.gemm(L.GEMM_DGRAD, st.dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bt.out_dim,
                rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1], impl=impl)
@@ -577,8 +577,7 @@ class Model:
     for i in range(len(trunk) - 1, -1, -1):
       s = trunk[i]
       xin = st.feat if i == 0 else st.acts[i - 1]
-      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(s, g), m=s.in_pad, n=W, k=M, impl=impl)
-      ops.colsum(cur, W, mlp.b(s, g))
+      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(s, g), m=s.in_pad, n=W, k=M, bias_grad=mlp.b(s, g), impl=impl)
       if i > 0:
         # only the hidden part of the input carries gradient (features are constants:
         # stop_gradient(sdist), models.py:200-201)

@@ -112,7 +112,7 @@ def viewdir_enc(viewdirs, num_samples, deg, out, col0, col_end):
 
 
 def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv=None, mask=None,
-         maskbits=None, impl=0):
+         maskbits=None, bias_grad=None, impl=0):
   """Dense-layer GEMM (see include/mnrf.h).  a/b/out/mask are 2-D views with unit inner stride."""
   lib = L.load()
   for t in (a, b, out) + ((mask,) if mask is not None else ()):
@@ -128,7 +128,7 @@ def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev[0].record()
   L.check(lib.mnrf_gemm(C.byref(d), L.ptr(a), L.ptr(b), L.ptr(bias), L.ptr(rowv), L.ptr(colv),
-                        L.ptr(mask), L.ptr(maskbits), L.ptr(out), L.stream_ptr()))
+                        L.ptr(mask), L.ptr(maskbits), L.ptr(bias_grad), L.ptr(out), L.stream_ptr()))
   if ev is not None:
     ev[1].record()
     GEMM_EVENTS.append((ev[0], ev[1], 2.0 * m * n * k))

@@ -350,9 +350,14 @@ def test_gemm_wgrad(ops, impl, R, Mo, N):
   dy = _bf(rng.normal(size=(R, N)).astype(np.float32))
   ref = x.float().T @ dy.float()
   out = torch.ones(Mo, N, device='cuda')          # accumulates into existing contents
-  ops.gemm(L.GEMM_WGRAD, x.cuda(), dy.cuda(), out, m=Mo, n=N, k=R, impl=impl)
+  db = torch.full((N,), 2.0, device='cuda')
+  ops.gemm(L.GEMM_WGRAD, x.cuda(), dy.cuda(), out, m=Mo, n=N, k=R, bias_grad=db, impl=impl)
   torch.cuda.synchronize()
   close(out, ref + 1.0, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad impl={impl}')
+  close(db, dy.float().sum(0) + 2.0, atol=1e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad bias grad impl={impl}')
+  out2 = torch.zeros(Mo, N, device='cuda')
+  ops.gemm(L.GEMM_WGRAD, x.cuda(), dy.cuda(), out2, m=Mo, n=N, k=R, impl=impl)
+  close(out2, ref, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad (no bias grad) impl={impl}')
 
 
 def test_heads_and_colsum(ops):
