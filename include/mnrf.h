@@ -126,23 +126,25 @@ typedef struct {
 /* maskbits (optional): 1-bit ReLU masks, word w of row m covers columns [32w, 32w+32).  FWD with
  * MNRF_ACT_RELU writes them (bit = output > 0); DGRAD reads them instead of the bf16 `mask`
  * (16x less mask traffic).  The caller zero-fills nothing: every word of the tile is written.
- * bias_grad (optional, WGRAD only): db[N] += column sums of B (= dY), computed from the B tiles
- * already staged in shared memory -- no separate pass over dY. */
+ * colsum (optional, DGRAD only): colsum[N] += column sums of the output, i.e. the bias gradient
+ * of the layer whose activation masks this dgrad; reduced from the epilogue registers (fp32,
+ * before the bf16 rounding of the stored output) -- no separate pass over dY. */
 int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
               const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-              float* bias_grad, void* out, mnrf_stream stream);
+              float* colsum, void* out, mnrf_stream stream);
 
 /* ---- small heads (N <= 4 outputs): density / rgb / predicted normals ---------------------
  * raw[M, n_out] = X[M, K](bf16) * W[n_out, K](bf16) + b, fp32 accumulate; models.py:460,585.
  * Backward: dX[M, K] (bf16, optionally relu-masked by X > 0; optional accumulate is not
  * provided -- the trunk adds the density term through mnrf_gemm's rowv/colv),
- * dW[K, n_out] += (the fp32 master layout [in, out]), db[n_out] += (fp32 atomics).
+ * dW[K, n_out] += (the fp32 master layout [in, out]), db[n_out] += (fp32 atomics);
+ * dxsum[K] += column sums of dX (optional: bias gradient of the layer that produced X).
  */
 int mnrf_head_fwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
                   const mnrf_bf16* w, const float* b, float* raw, mnrf_stream stream);
 int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
                   const mnrf_bf16* w, const float* draw, mnrf_bf16* dx, int64_t lddx,
-                  int32_t relu_mask, float* dw, float* db, mnrf_stream stream);
+                  int32_t relu_mask, float* dw, float* db, float* dxsum, mnrf_stream stream);
 
 /* Column sums of a bf16 matrix into fp32 (bias gradients): out[N] += sum_m x[m, :]. */
 int mnrf_colsum(int64_t m, int32_t n, const mnrf_bf16* x, int64_t ldx, float* out,

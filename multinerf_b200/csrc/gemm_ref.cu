@@ -8,7 +8,7 @@ namespace mnrf {
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                    const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                   float* bias_grad, void* out, cudaStream_t stream);
+                   float* colsum, void* out, cudaStream_t stream);
 
 __device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
@@ -76,18 +76,15 @@ __global__ void gemm_ref_tn_kernel(mnrf_gemm_desc d, const __nv_bfloat16* __rest
 
 extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                          const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                         float* bias_grad, void* out, mnrf_stream stream) {
+                         float* colsum, void* out, mnrf_stream stream) {
   using namespace mnrf;
   MNRF_CHECK(d && a && b && out, "mnrf_gemm: null pointer");
   MNRF_CHECK(d->mode >= 0 && d->mode <= 2, "mnrf_gemm: unknown mode %d", d->mode);
   MNRF_CHECK((rowv == nullptr) == (colv == nullptr), "mnrf_gemm: rowv and colv come together");
   if (d->m == 0 || d->n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, maskbits, bias_grad, out, s);
-  if (bias_grad) {
-    MNRF_CHECK(d->mode == MNRF_GEMM_WGRAD, "mnrf_gemm: bias_grad is a WGRAD output");
-    if (int rc = mnrf_colsum(d->k, d->n, b, d->ldb, bias_grad, stream)) return rc;
-  }
+  if (colsum) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD, "mnrf_gemm: colsum is a DGRAD output");
+  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, maskbits, colsum, out, s);
   dim3 block(16, 16);
   if (d->mode != MNRF_GEMM_WGRAD) {
     dim3 grid((d->n + 15) / 16, (unsigned)((d->m + 15) / 16));
@@ -99,6 +96,10 @@ extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf
                                                reinterpret_cast<const __nv_bfloat16*>(b), bias, rowv, colv,
                                                reinterpret_cast<const __nv_bfloat16*>(mask), maskbits,
                                                reinterpret_cast<__nv_bfloat16*>(out));
+    MNRF_LAUNCH_CHECK();
+    if (colsum) {   // reference path: sum the (bf16-rounded) output in a second pass
+      if (int rc = mnrf_colsum(d->m, d->n, reinterpret_cast<const mnrf_bf16*>(out), d->ldc, colsum, stream)) return rc;
+    }
   } else {
     int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, d->k / 4096));
     int rpb = (int)(((d->k + splits - 1) / splits + 15) / 16 * 16);

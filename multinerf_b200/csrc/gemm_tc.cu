@@ -182,7 +182,8 @@ struct GemmParams {
   uint32_t* maskbits;         // FWD+ReLU: written (1 bit per output, word = 32 columns); DGRAD: read
   int64_t ldmaskbits;         // in 32-bit words
   int use_tma_store;
-  float* bias_grad;           // WGRAD: db[N] += column sums of B (= dY), folded into the main loop
+  float* colsum;              // DGRAD: colsum[N] += column sums of the output (bias gradient of the
+                              // layer that produced the masking activation), from the epilogue registers
   void* out;
 };
 
@@ -213,9 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (MODE != MNRF_GEMM_WGRAD) prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && elect_one()) {
-    // WGRAD with a bias gradient: the 4 epilogue warps also consume every smem stage (column sums)
-    const uint32_t empty_count = (kWgrad && p.bias_grad) ? 1 + 4 : 1;
-    for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], empty_count); }
+    for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < NUM_ACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
     fence_barrier_init();
   }
@@ -306,44 +305,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     int it = 0;
     uint32_t out_group = 0;                 // running count of 64-column groups stored by this warp
-    uint32_t cstage = 0, cphase = 0;        // WGRAD bias-gradient companion loop over the smem ring
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile % p.num_n_blocks;
       const int rest = tile / p.num_n_blocks;
       const int m_blk = rest % p.num_m_blocks;
-      if (kWgrad && p.bias_grad) {
-        // db[n] += sum_r dY[r, n]: the B stage already sits in shared memory (MN-major, SW128:
-        // 64-column atoms 8 KiB apart, row r at r*128 B, 16-byte chunk c at position c ^ (r & 7)).
-        // Thread t of the 128 epilogue threads owns columns 2t, 2t+1; only the m_blk == 0 tiles sum
-        // (every other m_blk sees the same dY), all tiles release the stage.
-        const int split = rest / p.num_m_blocks;
-        const int kb0 = split * p.kblocks_per_split;
-        const int kb1 = min(p.num_k_blocks, kb0 + p.kblocks_per_split);
-        const int colp = 2 * ((warp - 4) * 32 + lane);
-        const bool do_sum = (m_blk == 0) && colp < p.block_n;
-        const uint32_t boff = (uint32_t)(colp >> 6) * (BLOCK_K * 128) + (uint32_t)((colp & 7) * 2);
-        const int chunk = (colp & 63) >> 3;
-        float s0 = 0.f, s1 = 0.f;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[cstage], cphase, 5);
-          if (do_sum) {
-            const uint8_t* sb = smem_b + cstage * B_STAGE_BYTES + boff;
-#pragma unroll 16
-            for (int r = 0; r < BLOCK_K; ++r) {
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(sb + r * 128 + ((chunk ^ (r & 7)) << 4));
-              s0 += bf16_lo(w);
-              s1 += bf16_hi(w);
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[cstage]);
-          if (++cstage == NUM_STAGES) { cstage = 0; cphase ^= 1; }
-        }
-        if (do_sum) {
-          atomicAdd(p.bias_grad + n_blk * p.block_n + colp, s0);
-          atomicAdd(p.bias_grad + n_blk * p.block_n + colp + 1, s1);
-        }
-      }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t row = (int64_t)m_blk * BLOCK_M + q * 32 + lane;
@@ -446,6 +411,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
+        }
+        if (MODE == MNRF_GEMM_DGRAD && p.colsum && c0 + 32 <= p.block_n) {
+          // Column sums over this warp's 32 rows by a shuffle transpose-reduce: each stage halves
+          // the values a lane holds; after 5 stages lane j owns column j.  Rows past M hold zeros
+          // (TMA zero-fills the A tile, rv = 0).
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = v[j];
+#pragma unroll
+          for (int sh = 16, n = 32; sh >= 1; sh >>= 1, n >>= 1) {
+            const bool up = (lane & sh) != 0;
+#pragma unroll
+            for (int i = 0; i < n / 2; ++i) {
+              const float send = up ? t[i] : t[i + n / 2];
+              const float keep = up ? t[i + n / 2] : t[i];
+              t[i] = keep + __shfl_xor_sync(0xffffffffu, send, sh);
+            }
+          }
+          atomicAdd(p.colsum + col + lane, t[0]);
         }
         uint4 o[4];
 #pragma unroll
@@ -551,7 +535,7 @@ static int pick_block_n(int n) {
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                    const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                   float* bias_grad, void* out, cudaStream_t stream) {
+                   float* colsum, void* out, cudaStream_t stream) {
   MNRF_CHECK(d->k % BLOCK_K == 0, "mnrf_gemm(tc): reduction length %d must be a multiple of %d", d->k, BLOCK_K);
   MNRF_CHECK(d->lda % 8 == 0 && d->ldb % 8 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0,
              "mnrf_gemm(tc): operands must be 16-byte aligned with ld %% 8 == 0");
@@ -570,8 +554,9 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   p.out = out;
   p.maskbits = maskbits;
   p.ldmaskbits = d->ldmaskbits;
-  p.bias_grad = bias_grad;
-  if (bias_grad) MNRF_CHECK(d->mode == MNRF_GEMM_WGRAD, "mnrf_gemm(tc): bias_grad is a WGRAD output");
+  p.colsum = colsum;
+  if (colsum) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD && p.block_n % 32 == 0,
+                         "mnrf_gemm(tc): colsum is a DGRAD output and needs N %% 32 == 0");
   if (maskbits) {
     MNRF_CHECK(d->mode != MNRF_GEMM_WGRAD, "mnrf_gemm(tc): maskbits make no sense for WGRAD");
     MNRF_CHECK(d->n % 32 == 0 && p.block_n % 32 == 0 && d->ldmaskbits * 32 >= d->n,

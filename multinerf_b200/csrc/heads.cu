@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(256)
 head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t ldx,
                 const __nv_bfloat16* __restrict__ w, const float* __restrict__ draw,
                 __nv_bfloat16* __restrict__ dx, int64_t lddx, int relu_mask,
-                float* __restrict__ dw, float* __restrict__ db, int64_t rows_per_block) {
+                float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dxsum,
+                int64_t rows_per_block) {
   extern __shared__ __align__(16) unsigned char smraw[];
   constexpr int n_out = N_OUT;
   float* sdw = reinterpret_cast<float*>(smraw);                                   // [n_out][K] fp32
@@ -77,6 +78,11 @@ head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t l
   float dbacc[N_OUT];
 #pragma unroll
   for (int o = 0; o < N_OUT; ++o) dbacc[o] = 0.f;
+  float xsum[kMaxChunks][8];       // column sums of dx over this thread's rows
+#pragma unroll
+  for (int q = 0; q < kMaxChunks; ++q)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xsum[q][e] = 0.f;
   for (int64_t m = m_begin + wib; m < m_end; m += nw) {
     float g[N_OUT];
 #pragma unroll
@@ -111,6 +117,8 @@ head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t l
 #pragma unroll
             for (int e = 0; e < 8; ++e) de[e] = xe[e] > 0.f ? de[e] : 0.f;
           }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xsum[q][e] += de[e];
           uint4 o4;
           o4.x = pack_bf16(de[0], de[1]); o4.y = pack_bf16(de[2], de[3]);
           o4.z = pack_bf16(de[4], de[5]); o4.w = pack_bf16(de[6], de[7]);
@@ -134,6 +142,28 @@ head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t l
       }
     }
     if (lane == 0 && db && dbacc[o] != 0.f) atomicAdd(&db[o], dbacc[o]);
+  }
+  if (dxsum) {
+    // reuse the dw staging buffer's first K floats once dw has been flushed
+    __syncthreads();
+    if (dw) for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) {
+      int o = i / K, k = i - o * K;
+      atomicAdd(&dw[(size_t)k * n_out + o], sdw[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sdw[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kMaxChunks; ++q) {
+      int c = lane + 32 * q;
+      if (c < K / 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&sdw[c * 8 + e], xsum[q][e]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(&dxsum[i], sdw[i]);
+    return;
   }
   __syncthreads();
   // dw is in the master layout [K, n_out] (row-major), the staging buffer is [n_out][K]
@@ -258,9 +288,10 @@ extern "C" int mnrf_head_fwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf1
 
 extern "C" int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
                              const mnrf_bf16* w, const float* draw, mnrf_bf16* dx, int64_t lddx,
-                             int32_t relu_mask, float* dw, float* db, mnrf_stream stream) {
+                             int32_t relu_mask, float* dw, float* db, float* dxsum, mnrf_stream stream) {
   using namespace mnrf;
   MNRF_CHECK(x && w && draw, "mnrf_head_bwd: null pointer");
+  MNRF_CHECK(!dxsum || dx, "mnrf_head_bwd: dxsum needs dx");
   MNRF_CHECK(n_out >= 1 && n_out <= kMaxHead, "mnrf_head_bwd: n_out %d not in [1,4]", n_out);
   MNRF_CHECK(k % 8 == 0 && k <= 1536 && ldx % 8 == 0 && (!dx || lddx % 8 == 0),
              "mnrf_head_bwd: K must be a multiple of 8 and <= 1536");
@@ -273,7 +304,7 @@ extern "C" int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf1
 #define MNRF_HB(NO, CK)                                                                         \
   head_bwd_kernel<NO, CK><<<blocks, 256, smem, (cudaStream_t)stream>>>(                         \
       m, k, reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(w), \
-      draw, reinterpret_cast<__nv_bfloat16*>(dx), lddx, relu_mask, dw, db, rpb)
+      draw, reinterpret_cast<__nv_bfloat16*>(dx), lddx, relu_mask, dw, db, dxsum, rpb)
 #define MNRF_HB_N(NO)                                      \
   do {                                                     \
     if (chunks <= 1) MNRF_HB(NO, 1);                       \

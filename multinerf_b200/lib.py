@@ -78,7 +78,7 @@ _SIGNATURES = {
     'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 10),
     'mnrf_head_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P, _P]),
     'mnrf_head_bwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P,
-                                C.c_int64, C.c_int32, _P, _P, _P]),
+                                C.c_int64, C.c_int32, _P, _P, _P, _P]),
     'mnrf_colsum': (C.c_int, [C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
     'mnrf_composite_fwd': (C.c_int, [C.POINTER(CompositeDesc)] + [_P] * 15),
     'mnrf_composite_bwd': (C.c_int, [C.POINTER(LossDesc)] + [_P] * 19),

@@ -523,7 +523,11 @@ class Model:
 
   # ------------------------------------------------------------------ backward
   def _mlp_backward(self, st: LevelState, mlp: MLPDevice, impl=0):
-    """Accumulates parameter gradients of one level into mlp.grads (fp32)."""
+    """Accumulates parameter gradients of one level into mlp.grads (fp32).
+
+    Bias gradients are column sums of the dY buffers; each is reduced inside the kernel that
+    PRODUCES that dY (DGRAD epilogue `colsum`, head_bwd `dxsum`), never by a separate pass.
+    """
     plan = mlp.plan
     cfg = plan.cfg
     M = st.B * st.S
@@ -533,6 +537,7 @@ class Model:
       st.dy = [torch.empty(M, W, device=dev, dtype=torch.bfloat16) for _ in range(2)]
     g = mlp.grads
     d = plan.by_role('density')[0]
+    trunk = plan.by_role('trunk')
     x_last = st.x_last
     dy = st.dy[0]
     d_raw_density = st.d_raw_density.view(M, 1)
@@ -540,49 +545,47 @@ class Model:
       r = plan.by_role('rgb')[0]
       views = plan.by_role('view')
       Wv = cfg.net_width_viewdirs
-      dv = torch.empty(M, Wv, device=dev, dtype=torch.bfloat16) if not hasattr(st, 'dv') else st.dv
-      st.dv = dv
-      v_last = st.vacts[-1]
-      ops.head_bwd(v_last, mlp.w_nk[r.name], st.d_raw_rgb.view(M, 3), r.out_dim, r.in_pad, dx=dv,
-                   relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g))
-      dcur = dv
+      if not hasattr(st, 'dv'):
+        st.dv = [torch.empty(M, Wv, device=dev, dtype=torch.bfloat16) for _ in range(min(2, len(views)))]
+      dcur = st.dv[0]
+      ops.head_bwd(st.vacts[-1], mlp.w_nk[r.name], st.d_raw_rgb.view(M, 3), r.out_dim, r.in_pad, dx=dcur,
+                   relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g), dxsum=mlp.b(views[-1], g))
       for i in range(len(views) - 1, -1, -1):
         s = views[i]
         xin = st.vin if i == 0 else st.vacts[i - 1]
-        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(s, g), m=s.in_pad, n=s.out_dim, k=M,
-                 bias_grad=mlp.b(s, g), impl=impl)
+        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(s, g), m=s.in_pad, n=s.out_dim, k=M, impl=impl)
         if i > 0:
-          nxt = torch.empty(M, Wv, device=dev, dtype=torch.bfloat16)
+          nxt = st.dv[1] if dcur is st.dv[0] else st.dv[0]
           ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s.name], nxt, m=M, n=Wv, k=s.out_dim,
-                   maskbits=st.vbits[i - 1], impl=impl)
+                   maskbits=st.vbits[i - 1], colsum=mlp.b(views[i - 1], g), impl=impl)
           dcur = nxt
       s0 = views[0]
       bt = plan.by_role('bottleneck')[0]
       if not hasattr(st, 'dbott'):
         st.dbott = torch.empty(M, bt.out_dim, device=dev, dtype=torch.bfloat16)
       # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
-      ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], st.dbott, m=M, n=bt.out_dim, k=s0.out_dim, impl=impl)
-      ops.gemm(L.GEMM_WGRAD, x_last, st.dbott, mlp.W(bt, g), m=bt.in_pad, n=bt.out_dim, k=M,
-               bias_grad=mlp.b(bt, g), impl=impl)
+      ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], st.dbott, m=M, n=bt.out_dim, k=s0.out_dim,
+               colsum=mlp.b(bt, g), impl=impl)
+      ops.gemm(L.GEMM_WGRAD, x_last, st.dbott, mlp.W(bt, g), m=bt.in_pad, n=bt.out_dim, k=M, impl=impl)
       # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
       ops.gemm(L.GEMM_DGRAD, st.dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bt.out_dim,
-               rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1], impl=impl)
+               rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1],
+               colsum=mlp.b(trunk[-1], g), impl=impl)
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=None, dw=mlp.W(d, g),
                    db=mlp.b(d, g))
     else:
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=dy, relu_mask=True,
-                   dw=mlp.W(d, g), db=mlp.b(d, g))
-    trunk = plan.by_role('trunk')
+                   dw=mlp.W(d, g), db=mlp.b(d, g), dxsum=mlp.b(trunk[-1], g))
     cur, other = st.dy[0], st.dy[1]
     for i in range(len(trunk) - 1, -1, -1):
       s = trunk[i]
       xin = st.feat if i == 0 else st.acts[i - 1]
-      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(s, g), m=s.in_pad, n=W, k=M, bias_grad=mlp.b(s, g), impl=impl)
+      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(s, g), m=s.in_pad, n=W, k=M, impl=impl)
       if i > 0:
         # only the hidden part of the input carries gradient (features are constants:
         # stop_gradient(sdist), models.py:200-201)
         ops.gemm(L.GEMM_DGRAD, cur, mlp.w_kn[s.name], other, m=M, n=W, k=W,
-                 maskbits=st.bits[i - 1], impl=impl)
+                 maskbits=st.bits[i - 1], colsum=mlp.b(trunk[i - 1], g), impl=impl)
         cur, other = other, cur
 
 

@@ -112,7 +112,7 @@ def viewdir_enc(viewdirs, num_samples, deg, out, col0, col_end):
 
 
 def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv=None, mask=None,
-         maskbits=None, bias_grad=None, impl=0):
+         maskbits=None, colsum=None, impl=0):
   """Dense-layer GEMM (see include/mnrf.h).  a/b/out/mask are 2-D views with unit inner stride."""
   lib = L.load()
   for t in (a, b, out) + ((mask,) if mask is not None else ()):
@@ -128,7 +128,7 @@ def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev[0].record()
   L.check(lib.mnrf_gemm(C.byref(d), L.ptr(a), L.ptr(b), L.ptr(bias), L.ptr(rowv), L.ptr(colv),
-                        L.ptr(mask), L.ptr(maskbits), L.ptr(bias_grad), L.ptr(out), L.stream_ptr()))
+                        L.ptr(mask), L.ptr(maskbits), L.ptr(colsum), L.ptr(out), L.stream_ptr()))
   if ev is not None:
     ev[1].record()
     GEMM_EVENTS.append((ev[0], ev[1], 2.0 * m * n * k))
@@ -146,13 +146,13 @@ def head_fwd(x, w_nk, bias, n_out, k, raw=None):
   return raw
 
 
-def head_bwd(x, w_nk, draw, n_out, k, dx=None, relu_mask=False, dw=None, db=None):
+def head_bwd(x, w_nk, draw, n_out, k, dx=None, relu_mask=False, dw=None, db=None, dxsum=None):
   lib = L.load()
   M = x.shape[0]
   _count()
   L.check(lib.mnrf_head_bwd(M, k, n_out, L.ptr(x), x.stride(0), L.ptr(w_nk), L.ptr(_f32(draw)),
                             L.ptr(dx), dx.stride(0) if dx is not None else 0, int(relu_mask),
-                            L.ptr(dw), L.ptr(db), L.stream_ptr()))
+                            L.ptr(dw), L.ptr(db), L.ptr(dxsum), L.stream_ptr()))
 
 
 def colsum(x, n, out):

@@ -331,10 +331,13 @@ def test_gemm_dgrad(ops, impl, M, N, K):
   words = (mb << torch.arange(32)).sum(-1)
   words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
   out2 = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+  cs = torch.full((N,), 3.0, device='cuda')
   ops.gemm(L.GEMM_DGRAD, dy.cuda(), w_kn.cuda(), out2, m=M, n=N, k=K, rowv=rowv.cuda(), colv=colv.cuda(),
-           maskbits=words.cuda(), impl=impl)
+           maskbits=words.cuda(), colsum=cs, impl=impl)
   torch.cuda.synchronize()
   close(out2.float(), ref.to(torch.bfloat16).float(), atol=3e-2, rtol=1.6e-2, msg=f'dgrad bits impl={impl}')
+  # fused bias gradient = column sums of the (fp32, pre-rounding) output, accumulated into cs
+  close(cs, ref.sum(0) + 3.0, atol=2e-2 * math.sqrt(M), rtol=2e-3, msg=f'dgrad colsum impl={impl}')
   out3 = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
   ops.gemm(L.GEMM_DGRAD, dy.cuda(), w_kn.cuda(), out3, m=M, n=N, k=K, impl=impl)
   close(out3.float(), (dy.float() @ w_kn.float().T).to(torch.bfloat16).float(), atol=3e-2, rtol=1.6e-2, msg='dgrad plain')
@@ -350,14 +353,9 @@ def test_gemm_wgrad(ops, impl, R, Mo, N):
   dy = _bf(rng.normal(size=(R, N)).astype(np.float32))
   ref = x.float().T @ dy.float()
   out = torch.ones(Mo, N, device='cuda')          # accumulates into existing contents
-  db = torch.full((N,), 2.0, device='cuda')
-  ops.gemm(L.GEMM_WGRAD, x.cuda(), dy.cuda(), out, m=Mo, n=N, k=R, bias_grad=db, impl=impl)
+  ops.gemm(L.GEMM_WGRAD, x.cuda(), dy.cuda(), out, m=Mo, n=N, k=R, impl=impl)
   torch.cuda.synchronize()
   close(out, ref + 1.0, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad impl={impl}')
-  close(db, dy.float().sum(0) + 2.0, atol=1e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad bias grad impl={impl}')
-  out2 = torch.zeros(Mo, N, device='cuda')
-  ops.gemm(L.GEMM_WGRAD, x.cuda(), dy.cuda(), out2, m=Mo, n=N, k=R, impl=impl)
-  close(out2, ref, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad (no bias grad) impl={impl}')
 
 
 def test_heads_and_colsum(ops):
@@ -372,8 +370,10 @@ def test_heads_and_colsum(ops):
     dx = torch.empty(M, K, dtype=torch.bfloat16, device='cuda')
     dw = torch.zeros(K, n_out, device='cuda')
     db = torch.zeros(n_out, device='cuda')
-    ops.head_bwd(x.cuda(), w.cuda(), draw.cuda(), n_out, K, dx=dx, relu_mask=True, dw=dw, db=db)
+    dxsum = torch.ones(K, device='cuda')
+    ops.head_bwd(x.cuda(), w.cuda(), draw.cuda(), n_out, K, dx=dx, relu_mask=True, dw=dw, db=db, dxsum=dxsum)
     ref_dx = (draw @ w.float()) * (x.float() > 0)
+    close(dxsum, ref_dx.sum(0) + 1.0, atol=2e-3 * math.sqrt(M), rtol=1e-4, msg='head dxsum')
     close(dx.float(), ref_dx.to(torch.bfloat16).float(), atol=1e-2, rtol=1e-2, msg='head dx')
     close(dw, x.float().T @ draw, atol=2e-3, rtol=1e-4, msg='head dw')
     close(db, draw.sum(0), atol=1e-3, rtol=1e-4, msg='head db')
