@@ -127,7 +127,7 @@ def run_ours(args):
   assert B_global % world == 0
   B = B_global // world
   model, variables = models.construct_model(2, None, bundle, device=dev)
-  step_fn = train_utils.create_train_step(model, bundle.config)
+  step_fn = train_utils.create_train_step(model, bundle.config, use_graph=not args.no_graph)
   state = train_utils.TrainState(variables)
   gen = torch.Generator(device=dev)
   gen.manual_seed(1234 + rank)
@@ -187,8 +187,11 @@ def run_ours(args):
 
   # dominant kernel (tcgen05 GEMM, all three modes): CUDA events around every launch of one
   # extra step; achieved = canonical train FLOPs of the step / time spent inside the GEMMs
+  eager_fn = train_utils.create_train_step(model, bundle.config, use_graph=False)
   ops.GEMM_EVENTS = []
-  timed(1, False)
+  barrier()
+  state, _, _ = eager_fn(gen, state, resident[0], None, 0.5)
+  barrier()
   evs = ops.GEMM_EVENTS
   ops.GEMM_EVENTS = None
   torch.cuda.synchronize()
@@ -212,6 +215,7 @@ def run_ours(args):
       'config': {'workload': 'mip-NeRF 360 (360.gin) train step: %d rays x (64+64+32) samples, '
                              'PropMLP 4x256, NerfMLP 8x1024' % B_global,
                  'global_batch': B_global, 'rays_per_gpu': B, 'parallelism': f'dp{world}',
+                 'cuda_graphs': not args.no_graph,
                  'l2_flush': 'not needed: >10 GB of activations streamed per step (L2 = 126 MB)'},
       'e2e': {'value': rays_per_s_e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d_bytes * world),
               'd2h_bytes_per_step': int(loss_host.numel() * 4 * world) if loss_host is not None else 0,
@@ -326,6 +330,7 @@ def main():
   ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
   ap.add_argument('--cpu_rays', type=int, default=256)
   ap.add_argument('--no_cpu_baseline', action='store_true')
+  ap.add_argument('--no_graph', action='store_true', help='launch every kernel from Python (no CUDA graphs)')
   args = ap.parse_args()
   if args.impl == 'reference':
     if args.steps > 3:

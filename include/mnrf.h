@@ -65,6 +65,11 @@ int mnrf_sample_level(const mnrf_sample_desc* d, const float* sdist_prev, const 
                       const float* u_base, const float* jitter, const float* cw_in,
                       float* sdist_out, int32_t* idx_out, float* cw_out, float* tdil_out,
                       float* wdil_out, mnrf_stream stream);
+/* Same, but the annealing exponent is read from device memory (`anneal_dev[0]`) at run time so
+ * that a captured CUDA graph can be replayed while train_frac advances (models.py:174-179). */
+int mnrf_sample_level_dyn(const mnrf_sample_desc* d, const float* sdist_prev, const float* w_prev,
+                          const float* u_base, const float* jitter, const float* anneal_dev,
+                          float* sdist_out, mnrf_stream stream);
 
 /* ---- ray casting + integrated positional encoding ------------------------------------
  * Replaces coord.construct_ray_warps s_to_t (coord.py:63-99), render.cast_rays
@@ -222,6 +227,9 @@ typedef struct {
 
 int mnrf_clip_adam(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
                    float* nu, float* norm_sq_scratch, mnrf_stream stream);
+/* Same, but (lr, 1-beta1^t, 1-beta2^t) are read from device memory `dyn[0..2]` (graph replay). */
+int mnrf_clip_adam_dyn(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
+                       float* nu, float* norm_sq_scratch, const float* dyn, mnrf_stream stream);
 
 /* fp32 master [in_pad, out] (row-major) -> bf16 shadows: w_nk [out, in_pad] (K-major operand
  * of the forward GEMM) and w_kn [in_pad, out] (K-major operand of the dgrad GEMM). */

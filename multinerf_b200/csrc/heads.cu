@@ -246,11 +246,13 @@ grad_norm_kernel(int64_t n, const float* __restrict__ g, float scale, float max_
 
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(mnrf_adam_desc d, float* __restrict__ p, const float* __restrict__ g,
-                 float* __restrict__ mu, float* __restrict__ nu, const float* __restrict__ norm_sq) {
+                 float* __restrict__ mu, float* __restrict__ nu, const float* __restrict__ norm_sq,
+                 const float* __restrict__ dyn) {
   float mult = 1.f;
   if (d.grad_max_norm > 0.f) mult = fminf(1.f, d.grad_max_norm / (kEps + sqrtf(*norm_sq)));
-  const float bc1 = 1.f - powf(d.beta1, (float)d.step);
-  const float bc2 = 1.f - powf(d.beta2, (float)d.step);
+  float bc1 = 1.f - powf(d.beta1, (float)d.step);
+  float bc2 = 1.f - powf(d.beta2, (float)d.step);
+  if (dyn) { d.lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = g[i] * d.grad_scale;
     if (d.grad_max_val > 0.f) v = fminf(fmaxf(v, -d.grad_max_val), d.grad_max_val);
@@ -352,8 +354,8 @@ extern "C" int mnrf_pack_weights(int32_t in_pad, int32_t out, const float* maste
   return 0;
 }
 
-extern "C" int mnrf_clip_adam(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
-                              float* nu, float* norm_sq_scratch, mnrf_stream stream) {
+static int clip_adam_impl(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
+                          float* nu, float* norm_sq_scratch, const float* dyn, mnrf_stream stream) {
   using namespace mnrf;
   MNRF_CHECK(d && params && grads && mu && nu && norm_sq_scratch, "mnrf_clip_adam: null pointer");
   MNRF_CHECK(d->step >= 1, "mnrf_clip_adam: step is the 1-based update count");
@@ -365,7 +367,18 @@ extern "C" int mnrf_clip_adam(const mnrf_adam_desc* d, float* params, const floa
     grad_norm_kernel<<<blocks, 256, 0, s>>>(d->n, grads, d->grad_scale, d->grad_max_val, norm_sq_scratch);
     MNRF_LAUNCH_CHECK();
   }
-  clip_adam_kernel<<<blocks, 256, 0, s>>>(*d, params, grads, mu, nu, norm_sq_scratch);
+  clip_adam_kernel<<<blocks, 256, 0, s>>>(*d, params, grads, mu, nu, norm_sq_scratch, dyn);
   MNRF_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mnrf_clip_adam(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
+                              float* nu, float* norm_sq_scratch, mnrf_stream stream) {
+  return clip_adam_impl(d, params, grads, mu, nu, norm_sq_scratch, nullptr, stream);
+}
+
+extern "C" int mnrf_clip_adam_dyn(const mnrf_adam_desc* d, float* params, const float* grads, float* mu,
+                                  float* nu, float* norm_sq_scratch, const float* dyn, mnrf_stream stream) {
+  MNRF_CHECK(dyn, "mnrf_clip_adam_dyn: null dyn");
+  return clip_adam_impl(d, params, grads, mu, nu, norm_sq_scratch, dyn, stream);
 }

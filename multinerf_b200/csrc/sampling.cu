@@ -36,8 +36,9 @@ sample_level_kernel(mnrf_sample_desc d, const float* __restrict__ sdist_prev,
                     const float* __restrict__ jitter, const float* __restrict__ cw_in,
                     float* __restrict__ sdist_out, int32_t* __restrict__ idx_out,
                     float* __restrict__ cw_out, float* __restrict__ tdil_out,
-                    float* __restrict__ wdil_out) {
+                    float* __restrict__ wdil_out, const float* __restrict__ anneal_dev) {
   extern __shared__ float smem[];
+  if (anneal_dev) d.anneal = *anneal_dev;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int P = d.num_prev, S = d.num_samples;
@@ -203,11 +204,11 @@ sample_level_kernel(mnrf_sample_desc d, const float* __restrict__ sdist_prev,
 
 }  // namespace mnrf
 
-extern "C" int mnrf_sample_level(const mnrf_sample_desc* d, const float* sdist_prev,
-                                 const float* w_prev, const float* u_base, const float* jitter,
-                                 const float* cw_in, float* sdist_out, int32_t* idx_out,
-                                 float* cw_out, float* tdil_out, float* wdil_out,
-                                 mnrf_stream stream) {
+static int sample_level_impl(const mnrf_sample_desc* d, const float* sdist_prev,
+                             const float* w_prev, const float* u_base, const float* jitter,
+                             const float* cw_in, float* sdist_out, int32_t* idx_out,
+                             float* cw_out, float* tdil_out, float* wdil_out,
+                             const float* anneal_dev, mnrf_stream stream) {
   using namespace mnrf;
   MNRF_CHECK(d && sdist_prev && w_prev && u_base && sdist_out, "mnrf_sample_level: null pointer");
   MNRF_CHECK(d->num_samples > 1, "num_samples must be > 1, is %d.", d->num_samples);
@@ -229,7 +230,24 @@ extern "C" int mnrf_sample_level(const mnrf_sample_desc* d, const float* sdist_p
   const int max_blocks = mnrf_num_sms() * 16;
   if (blocks > max_blocks) blocks = max_blocks;
   sample_level_kernel<<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(
-      *d, sdist_prev, w_prev, u_base, jitter, cw_in, sdist_out, idx_out, cw_out, tdil_out, wdil_out);
+      *d, sdist_prev, w_prev, u_base, jitter, cw_in, sdist_out, idx_out, cw_out, tdil_out, wdil_out,
+      anneal_dev);
   MNRF_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mnrf_sample_level(const mnrf_sample_desc* d, const float* sdist_prev,
+                                 const float* w_prev, const float* u_base, const float* jitter,
+                                 const float* cw_in, float* sdist_out, int32_t* idx_out,
+                                 float* cw_out, float* tdil_out, float* wdil_out,
+                                 mnrf_stream stream) {
+  return sample_level_impl(d, sdist_prev, w_prev, u_base, jitter, cw_in, sdist_out, idx_out, cw_out,
+                           tdil_out, wdil_out, nullptr, stream);
+}
+
+extern "C" int mnrf_sample_level_dyn(const mnrf_sample_desc* d, const float* sdist_prev,
+                                     const float* w_prev, const float* u_base, const float* jitter,
+                                     const float* anneal_dev, float* sdist_out, mnrf_stream stream) {
+  return sample_level_impl(d, sdist_prev, w_prev, u_base, jitter, nullptr, sdist_out, nullptr, nullptr,
+                           nullptr, nullptr, anneal_dev, stream);
 }

@@ -72,6 +72,7 @@ _SIGNATURES = {
     'mnrf_device_ok': (C.c_int, []),
     'mnrf_num_sms': (C.c_int, []),
     'mnrf_sample_level': (C.c_int, [C.POINTER(SampleDesc)] + [_P] * 11),
+    'mnrf_sample_level_dyn': (C.c_int, [C.POINTER(SampleDesc)] + [_P] * 7),
     'mnrf_encode': (C.c_int, [C.POINTER(EncodeDesc)] + [_P] * 11),
     'mnrf_viewdir_enc': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),
@@ -83,6 +84,7 @@ _SIGNATURES = {
     'mnrf_composite_fwd': (C.c_int, [C.POINTER(CompositeDesc)] + [_P] * 15),
     'mnrf_composite_bwd': (C.c_int, [C.POINTER(LossDesc)] + [_P] * 19),
     'mnrf_clip_adam': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 6),
+    'mnrf_clip_adam_dyn': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 7),
     'mnrf_pack_weights': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
 EXPORTED = tuple(_SIGNATURES)

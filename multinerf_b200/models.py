@@ -435,7 +435,7 @@ class Model:
     r.far_flat = r.far[:, 0].contiguous()
     return r
 
-  def forward_levels(self, rng, rays, train_frac, compute_extras, want_samples, impl=0):
+  def forward_levels(self, rng, rays, train_frac, compute_extras, want_samples, impl=0, anneal_dev=None):
     """Runs all levels; returns the list of LevelState (buffers stay valid until the next call)."""
     if self.params is None:
       raise RuntimeError('Model has no parameters: call construct_model()/init() first')
@@ -466,7 +466,7 @@ class Model:
       ops.sample_level(sdist_prev, w_prev, lv['S'], dilation=lv['dilation'],
                        use_dilation=lv['use_dilation'], domain=(s_near, s_far), anneal=lv['anneal'],
                        resample_padding=m.resample_padding, jitter=jit, single_jitter=m.single_jitter,
-                       u_base=u_base, max_jitter=max_jitter, out=st.sdist)
+                       u_base=u_base, max_jitter=max_jitter, out=st.sdist, anneal_dev=anneal_dev)
       self._mlp_forward(st, mlp, rays, impl=impl)
       st.noise = None
       if mlp.plan.cfg.density_noise > 0 and rng is not None:

@@ -43,7 +43,7 @@ def u_grid(num_samples, randomized):
 def sample_level(sdist_prev, w_prev, num_samples, *, dilation=0.0, use_dilation=False,
                  domain=(0.0, 1.0), anneal=1.0, resample_padding=0.0, jitter=None,
                  single_jitter=True, u_base=None, max_jitter=None, cw_in=None, want_index=False,
-                 want_debug=False, out=None):
+                 want_debug=False, out=None, anneal_dev=None):
   """One level of hierarchical resampling -> sdist [B, S+1] (+ int32 idx, debug arrays)."""
   lib = L.load()
   if num_samples <= 1:
@@ -65,6 +65,12 @@ def sample_level(sdist_prev, w_prev, num_samples, *, dilation=0.0, use_dilation=
   tdil = torch.empty(B, nb + 1, device=dev) if want_debug else None
   wdil = torch.empty(B, nb, device=dev) if want_debug else None
   _count()
+  if anneal_dev is not None:
+    assert cw_in is None and not want_index and not want_debug
+    L.check(lib.mnrf_sample_level_dyn(C.byref(d), L.ptr(_f32(sdist_prev)), L.ptr(_f32(w_prev)),
+                                      L.ptr(_f32(u_base)), L.ptr(_f32(jitter)), L.ptr(anneal_dev),
+                                      L.ptr(sdist), L.stream_ptr()))
+    return sdist
   L.check(lib.mnrf_sample_level(C.byref(d), L.ptr(_f32(sdist_prev)), L.ptr(_f32(w_prev)),
                                 L.ptr(_f32(u_base)), L.ptr(_f32(jitter)), L.ptr(_f32(cw_in)),
                                 L.ptr(sdist), L.ptr(idx), L.ptr(cw), L.ptr(tdil), L.ptr(wdil),
@@ -220,11 +226,15 @@ def composite_bwd(raw_density, raw_rgb, sdist, directions, near, far, target_rgb
 
 
 def clip_adam(params, grads, mu, nu, scratch, *, step, lr, beta1, beta2, eps, grad_max_val,
-              grad_max_norm, grad_scale=1.0):
+              grad_max_norm, grad_scale=1.0, dyn=None):
   lib = L.load()
   d = L.AdamDesc(params.numel(), float(grad_max_val), float(grad_max_norm), float(lr), float(beta1),
                  float(beta2), float(eps), int(step), float(grad_scale))
   _count(2 if grad_max_norm > 0 else 1)
+  if dyn is not None:
+    L.check(lib.mnrf_clip_adam_dyn(C.byref(d), L.ptr(params), L.ptr(grads), L.ptr(mu), L.ptr(nu),
+                                   L.ptr(scratch), L.ptr(dyn), L.stream_ptr()))
+    return
   L.check(lib.mnrf_clip_adam(C.byref(d), L.ptr(params), L.ptr(grads), L.ptr(mu), L.ptr(nu),
                              L.ptr(scratch), L.stream_ptr()))
 

@@ -55,8 +55,21 @@ class TrainState:
 STAT_NAMES = ('data', 'mse', 'distortion', 'interlevel')
 
 
-def create_train_step(model: models.Model, config: configs.Config, impl=0):
-  """Returns train_pstep (train_utils.py:221-346) for this rank's shard of the batch."""
+def _anneal(mcfg, train_frac):
+  if mcfg.anneal_slope > 0:
+    sl = mcfg.anneal_slope
+    return (sl * train_frac) / ((sl - 1) * train_frac + 1)
+  return 1.0
+
+
+def create_train_step(model: models.Model, config: configs.Config, impl=0, use_graph=False):
+  """Returns train_pstep (train_utils.py:221-346) for this rank's shard of the batch.
+
+  use_graph=True captures the step into two CUDA graphs (forward+backward | clip+Adam+repack,
+  with the NCCL all-reduce between them) after one eager warm-up step; per-step scalars
+  (annealing exponent, learning rate, Adam bias corrections) and the jitter draws live in device
+  buffers that are refreshed before each replay, so train_frac and the step count may advance.
+  """
   mcfg = model.mcfg
   if config.data_loss_type not in ('mse', 'charb', 'rawnerf'):
     raise NotImplementedError(f'data_loss_type {config.data_loss_type!r}')
@@ -65,18 +78,19 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0):
     raise NotImplementedError('orientation / predicted-normal losses (Ref-NeRF) are a later milestone')
   if config.weight_decay_mults:
     raise NotImplementedError('weight_decay_mults')
+  if use_graph and mcfg.near_anneal_rate is not None:
+    use_graph = False          # init_s_near depends on train_frac by value
   dev = model.device
   stats_buf = torch.zeros(mcfg.num_levels, 8, device=dev)
   scratch = torch.zeros(4, device=dev)
+  dyn = torch.zeros(4, device=dev)               # lr, 1-b1^t, 1-b2^t
+  dyn_host = torch.zeros(4).pin_memory() if torch.cuda.is_available() else torch.zeros(4)
+  anneal_dev = torch.zeros(1, device=dev)
+  G = {'state': 0, 'fb': None, 'opt': None, 'rays': None, 'target': None, 'jitter': None,
+       'noise': None, 'launches': 0}
 
-  def train_step(rng, state, batch, cameras, train_frac, loss_threshold=1.0):
-    world, _ = _world()
-    params = state.params
-    if model.params is not params:
-      model.bind(params)
-    rays = batch.rays if hasattr(batch.rays, 'radii_flat') else model._prep_rays(batch.rays)
-    B = rays.origins.shape[0]
-    target = torch.as_tensor(batch.rgb).to(dev, torch.float32).reshape(B, -1)[:, :3].contiguous()
+  def fwd_bwd(rng, rays, target, train_frac, anneal_ptr):
+    params = model.params
     lossmult = rays.lossmult
     if config.disable_multiscale_loss:
       lossmult = torch.ones_like(lossmult)
@@ -85,7 +99,8 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0):
     params.grads.zero_()
     stats_buf.zero_()
     states = model.forward_levels(rng if config.randomized else None, rays, train_frac,
-                                  compute_extras=False, want_samples=False, impl=impl)
+                                  compute_extras=False, want_samples=False, impl=impl,
+                                  anneal_dev=anneal_ptr)
     fine = states[-1]
     n = len(states)
     for i in range(n - 1, -1, -1):
@@ -102,21 +117,114 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0):
           weights_fine=None if is_fine else fine.comp['weights'],
           density_noise=st.noise, d_raw_density=st.d_raw_density, d_raw_rgb=st.d_raw_rgb)
       model._mlp_backward(st, model.mlps[st.mname], impl=impl)
-    grad_scale = allreduce_mean_(params.grads, stats_buf, world)
+
+  def optim(grad_scale, step, lr, dyn_ptr):
+    params = model.params
+    for name in model.plans:
+      ops.clip_adam(params.seg(name), params.seg(name, params.grads), params.seg(name, params.mu),
+                    params.seg(name, params.nu), scratch, step=step, lr=lr,
+                    beta1=config.adam_beta1, beta2=config.adam_beta2, eps=config.adam_eps,
+                    grad_max_val=config.grad_max_val, grad_max_norm=config.grad_max_norm,
+                    grad_scale=grad_scale, dyn=dyn_ptr)
+    for mlp in model.mlps.values():
+      mlp.repack()
+
+  def set_dyn(step, lr):
+    dyn_host[0] = lr
+    dyn_host[1] = 1.0 - config.adam_beta1 ** step
+    dyn_host[2] = 1.0 - config.adam_beta2 ** step
+    dyn.copy_(dyn_host, non_blocking=True)
+
+  def draw_randomness(rng, B, sched):
+    """Explicit draws for this step (the reference splits a threefry key per level)."""
+    if rng is None or not config.randomized:
+      return None
+    jit = G['jitter']
+    if jit is None:
+      jit = [torch.empty((B,) if mcfg.single_jitter else (B, lv['S']), device=dev) for lv in sched]
+      G['jitter'] = jit
+      G['noise'] = [torch.empty(B, lv['S'], device=dev) for lv in sched]
+    out = {'jitter': jit}
+    need_noise = any(p.cfg.density_noise > 0 for p in model.plans.values())
+    if isinstance(rng, dict):        # explicit draws: stage them in the static buffers
+      for t, src in zip(jit, rng['jitter']):
+        t.copy_(torch.as_tensor(src).to(dev).reshape(t.shape), non_blocking=True)
+      if need_noise:
+        for t, src in zip(G['noise'], rng['density_noise']):
+          t.copy_(torch.as_tensor(src).to(dev).reshape(t.shape), non_blocking=True)
+    else:
+      for t in jit:
+        t.uniform_(0.0, 1.0, generator=rng)
+      if need_noise:
+        for t in G['noise']:
+          t.normal_(0.0, 1.0, generator=rng)
+    if need_noise:
+      out['density_noise'] = G['noise']
+    return out
+
+  def train_step(rng, state, batch, cameras, train_frac, loss_threshold=1.0):
+    world, _ = _world()
+    params = state.params
+    if model.params is not params:
+      model.bind(params)
+      G['state'] = 0
+    rays = batch.rays if hasattr(batch.rays, 'radii_flat') else model._prep_rays(batch.rays)
+    B = rays.origins.shape[0]
+    target = torch.as_tensor(batch.rgb).to(dev, torch.float32).reshape(B, -1)[:, :3].contiguous()
+    sched = model.level_schedule(train_frac)[2]
+    n = len(sched)
+    grad_scale = 1.0 / world
     params.step += 1
     lr = learning_rate_decay(params.step - 1, config.lr_init, config.lr_final, config.max_steps,
                              config.lr_delay_steps, config.lr_delay_mult)
-    for name in model.plans:
-      ops.clip_adam(params.seg(name), params.seg(name, params.grads), params.seg(name, params.mu),
-                    params.seg(name, params.nu), scratch, step=params.step, lr=lr,
-                    beta1=config.adam_beta1, beta2=config.adam_beta2, eps=config.adam_eps,
-                    grad_max_val=config.grad_max_val, grad_max_norm=config.grad_max_norm,
-                    grad_scale=grad_scale)
-    for mlp in model.mlps.values():
-      mlp.repack()
-    stats = LazyStats(stats_buf, n)
-    return state, stats, rng
+    if not use_graph or G['state'] == 0:
+      # eager step (also the warm-up that allocates every buffer before a capture)
+      fwd_bwd(draw_randomness(rng, B, sched) if use_graph else rng, rays, target, train_frac, None)
+      allreduce_mean_(params.grads, stats_buf, world)
+      optim(grad_scale, params.step, lr, None)
+      G['state'] = 1 if use_graph else 0
+      G['B'] = B
+      return state, LazyStats(stats_buf, n), rng
+    if G['B'] != B:
+      raise ValueError(f'graph mode needs a fixed batch size ({G["B"]} rays per rank), got {B}')
+    rand = draw_randomness(rng, B, sched)
+    anneal_dev.fill_(_anneal(mcfg, train_frac))
+    set_dyn(params.step, lr)
+    if G['state'] == 1:
+      # capture: inputs live in static buffers from now on
+      import dataclasses
+      G['rays'] = rays
+      G['rays'] = type(rays)(**{f.name: (None if getattr(rays, f.name) is None else getattr(rays, f.name).clone())
+                                for f in dataclasses.fields(rays)})
+      for extra in ('radii_flat', 'near_flat', 'far_flat'):
+        setattr(G['rays'], extra, getattr(rays, extra).clone())
+      G['target'] = target.clone()
+      torch.cuda.synchronize()
+      before = ops.LAUNCHES
+      G['fb'] = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(G['fb']):
+        fwd_bwd(rand, G['rays'], G['target'], train_frac, anneal_dev)
+      G['opt'] = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(G['opt']):
+        optim(grad_scale, params.step, lr, dyn)
+      G['launches'] = ops.LAUNCHES - before
+      G['state'] = 2
+    else:
+      import dataclasses
+      for f in dataclasses.fields(rays):
+        v = getattr(rays, f.name)
+        if v is not None:
+          getattr(G['rays'], f.name).copy_(v, non_blocking=True)
+      for extra in ('radii_flat', 'near_flat', 'far_flat'):
+        getattr(G['rays'], extra).copy_(getattr(rays, extra), non_blocking=True)
+      G['target'].copy_(target, non_blocking=True)
+    G['fb'].replay()
+    allreduce_mean_(params.grads, stats_buf, world)
+    G['opt'].replay()
+    ops.LAUNCHES += G['launches']
+    return state, LazyStats(stats_buf, n), rng
 
+  train_step.graph_info = G
   return train_step
 
 

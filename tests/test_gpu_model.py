@@ -195,3 +195,39 @@ def test_train_step_vs_oracle(mods, which, impl):
       assert float((a - b).abs().max()) <= 2.1 * lr, (mname, lname)
       agree = ((a - params0[mname][lname]['kernel']).sign() == (b - params0[mname][lname]['kernel']).sign())
       assert float(agree.float().mean()) > 0.95, (mname, lname, float(agree.float().mean()))
+
+
+def test_cuda_graph_train_step_matches_eager(mods):
+  """The captured two-graph step (forward+backward | clip+Adam+repack) must track the eager step
+  while train_frac, the learning rate, the Adam bias corrections and the jitter change per step."""
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  bundle = mini360()
+  B = 256
+  rays, rng = synth_rays(5, B, 0.2, 1e6)
+  sched_n = 3
+  steps = 5
+  batches = [(synth_rays(10 + i, B, 0.2, 1e6)[0], rng.uniform(0, 1, (B, 3)).astype(np.float32)) for i in range(steps)]
+  rands = [{'jitter': [torch.tensor(rng.uniform(0, 1, (B,)).astype(np.float32)) for _ in range(sched_n)]}
+           for _ in range(steps)]
+  results = []
+  for use_graph in [False, True]:
+    model, variables = models.construct_model(6, rays, bundle)
+    step_fn = train_utils.create_train_step(model, bundle.config, use_graph=use_graph)
+    state = train_utils.TrainState(variables)
+    losses = []
+    for i in range(steps):
+      r, tgt = batches[i]
+      state, stats, _ = step_fn(rands[i], state, utils.Batch(rays=r, rgb=tgt), None, i / 10.0)
+      losses.append(stats.materialize()['loss'])
+    torch.cuda.synchronize()
+    results.append((losses, variables.flat.clone(), variables.step))
+    if use_graph:
+      assert step_fn.graph_info['state'] == 2 and step_fn.graph_info['launches'] > 20
+  (l0, p0, s0), (l1, p1, s1) = results
+  assert s0 == s1 == steps
+  for a, b in zip(l0, l1):
+    assert abs(a - b) < 2e-3 * max(1.0, abs(a)), (l0, l1)
+  # fp32 atomics make the two runs differ in the last bits only
+  rel = float((p0 - p1).norm() / p0.norm())
+  assert rel < 2e-3, rel
