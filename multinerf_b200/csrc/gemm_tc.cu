@@ -7,7 +7,9 @@
 //   warp 0   : TMA producer (one elected lane) -- cp.async.bulk.tensor.2d into a 4-stage ring
 //   warp 1   : MMA issuer  (one elected lane) -- tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256
 //   warp 2   : TMEM allocator (512 columns = two 256-column accumulator stages)
-//   warps 4-7: epilogue -- tcgen05.ld 32x32b, bias/ReLU | mask/rank-1 | fp32 reduction, stores
+//   warps 4-11: epilogue -- two warps per TMEM lane quadrant (each takes half of the tile's
+//              columns): tcgen05.ld 32x32b, bias/ReLU | mask/rank-1/column sums | fp32 reduction,
+//              swizzled smem staging + TMA bulk stores
 //
 // Operand layouts (all bf16, 128-byte swizzle):
 //   FWD / DGRAD : A[M,K] and B[N,K] are K-major (reduction index contiguous);
@@ -31,11 +33,12 @@ constexpr int NUM_STAGES = 4;
 constexpr int NUM_ACC = 2;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KiB
-constexpr int OUT_STAGE_BYTES = 4 * 32 * 128;                // 4 epilogue warps x 32 rows x 128 B
-constexpr int NUM_OUT_STAGES = 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int OUT_STAGE_BYTES = NUM_EPI_WARPS * 32 * 128;    // one 32-row x 128-byte slab per epilogue warp
+constexpr int NUM_OUT_STAGES = 1;
 constexpr int SMEM_BYTES = NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_OUT_STAGES * OUT_STAGE_BYTES +
                            1024 /*align*/ + 256;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -215,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < NUM_ACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    for (int i = 0; i < NUM_ACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NUM_EPI_WARPS * 32); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -303,8 +306,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int ew = warp - 4;                // epilogue warp index 0..7
+    // the two warps of a quadrant split the tile's columns (tiles narrower than 128: warp-half 0 only)
+    const int cols_per_half = p.block_n >= 128 ? p.block_n / 2 : p.block_n;
+    const int c_begin = (ew >> 2) * cols_per_half;
+    const int c_end = min(p.block_n, c_begin + cols_per_half);
     int it = 0;
-    uint32_t out_group = 0;                 // running count of 64-column groups stored by this warp
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile % p.num_n_blocks;
       const int rest = tile / p.num_n_blocks;
@@ -331,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);
         const int col = ncol0 + c0;
@@ -442,10 +449,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.use_tma_store) {
           // 64-column groups: two 32-column halves share one 32x128-byte swizzled staging slab
           const int half = (c0 >> 5) & 1;
-          uint8_t* slab = smem_out + (out_group & 1) * OUT_STAGE_BYTES + q * (32 * 128);
+          uint8_t* slab = smem_out + ew * (32 * 128);
           if (half == 0) {
-            // the bulk store issued from this slab two groups ago must have finished reading it
-            if (lane == 0) tma_store_wait_read<NUM_OUT_STAGES - 1>();
+            // the bulk store previously issued from this slab must have finished reading it
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
           }
 #pragma unroll
@@ -460,7 +467,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_store_2d(&tmap_c, slab, ncol0 + c0 - 32, m_blk * BLOCK_M + q * 32);
               tma_store_commit();
             }
-            ++out_group;
           }
         } else if (row_ok) {
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col);
@@ -474,12 +480,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (MODE == MNRF_GEMM_FWD && p.act == MNRF_ACT_RELU && p.maskbits && row_ok) {
         uint32_t* mp = p.maskbits + row * p.ldmaskbits + (ncol0 >> 5);
         if (p.block_n == MAX_BLOCK_N) {
-          reinterpret_cast<uint4*>(mp)[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-          reinterpret_cast<uint4*>(mp)[1] = make_uint4(mbits[4], mbits[5], mbits[6], mbits[7]);
+          if (ew < 4) reinterpret_cast<uint4*>(mp)[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+          else reinterpret_cast<uint4*>(mp)[1] = make_uint4(mbits[4], mbits[5], mbits[6], mbits[7]);
         } else {
 #pragma unroll
           for (int w = 0; w < MAX_BLOCK_N / 32; ++w)
-            if (w * 32 < p.block_n) mp[w] = mbits[w];
+            if (w * 32 >= c_begin && w * 32 < c_end) mp[w] = mbits[w];
         }
       }
     }
