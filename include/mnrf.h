@@ -162,6 +162,8 @@ int mnrf_colsum(int64_t m, int32_t n, const mnrf_bf16* x, int64_t ldx, float* ou
  *   raw_density [B,S]; raw_rgb [B,S,3] or NULL (PropMLP: disable_rgb -> rgb = 0)
  *   density_noise optional [B,S] N(0,1) draws (models.py:462-464)
  *   sdist [B,S+1]; directions [B,3]; near/far [B]; bg: scalar or NULL->bg_rgb [B,3]
+ *   rgb_scale optional [B,3]: per-ray colour scale applied to the sample colours (RawNeRF
+ *   exposure_values x learned exposure scaling, models.py:257-267)
  *   outputs: weights [B,S]; rgb_out [B,3]; optional density_out [B,S], rgb_samples [B,S,3]
  *   extras (compute_extras): acc [B], dist [B,4] = (mean, p5, median, p95) or NULL
  */
@@ -179,8 +181,9 @@ typedef struct {
 int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw_density,
                        const float* raw_rgb, const float* density_noise, const float* sdist,
                        const float* directions, const float* near, const float* far,
-                       const float* bg_rgb, float* weights, float* rgb_out, float* density_out,
-                       float* rgb_samples, float* acc, float* dist, mnrf_stream stream);
+                       const float* bg_rgb, const float* rgb_scale, float* weights, float* rgb_out,
+                       float* density_out, float* rgb_samples, float* acc, float* dist,
+                       mnrf_stream stream);
 
 /* Losses + compositing backward for one level (train_utils.py:72-159 + the adjoint of
  * render.py:130-213).  Fuses: data loss (mse | charb | rawnerf) on this level's pixel,
@@ -206,11 +209,12 @@ typedef struct {
 int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_density, const float* raw_rgb,
                        const float* density_noise, const float* sdist, const float* directions,
                        const float* near, const float* far, const float* bg_rgb,
-                       const float* weights, const float* rgb_out, const float* target_rgb,
+                       const float* rgb_scale, const float* weights, const float* rgb_out,
+                       const float* target_rgb,
                        const float* lossmult, const float* inv_denom /* device scalar */,
                        const float* sdist_fine, const float* weights_fine,
-                       float* d_raw_density, float* d_raw_rgb, float* stats,
-                       mnrf_stream stream);
+                       float* d_raw_density, float* d_raw_rgb, float* d_rgb_scale /* [B,3] or NULL */,
+                       float* stats, mnrf_stream stream);
 
 /* ---- optimizer ---------------------------------------------------------------------------
  * train_utils.clip_gradients (train_utils.py:200-218: value clip, then global-norm clip with

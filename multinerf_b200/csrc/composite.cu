@@ -21,8 +21,9 @@ struct RayState {
   float w[CH];      // alpha * T
   float dens_in[CH];  // raw + bias (+ noise): argument of softplus
   float delta[CH];
-  float c[CH][3];   // activated + padded colour
+  float c[CH][3];   // activated + padded colour, times the per-ray exposure scale
   float z[CH][3];   // premult * raw + bias (argument of the rgb activation)
+  float sc[3];      // per-ray rgb scale (RawNeRF exposure, models.py:257-267); 1 if absent
   float acc;        // sum of w
 };
 
@@ -40,9 +41,12 @@ __device__ __forceinline__ void ray_forward(const mnrf_composite_desc& d, int ra
                                             const float* __restrict__ raw_density,
                                             const float* __restrict__ raw_rgb,
                                             const float* __restrict__ density_noise,
+                                            const float* __restrict__ rgb_scale,
                                             const float* tds, float dnorm, RayState<CH>& st) {
   const int S = d.num_samples;
   float local = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) st.sc[ch] = rgb_scale ? rgb_scale[ray * 3 + ch] : 1.f;
 #pragma unroll
   for (int j = 0; j < CH; ++j) {
     int s = lane * CH + j;
@@ -63,7 +67,7 @@ __device__ __forceinline__ void ray_forward(const mnrf_composite_desc& d, int ra
       float z = 0.f, c = 0.f;
       if (raw_rgb && ok) {
         z = d.rgb_premult * raw_rgb[((size_t)ray * S + s) * 3 + ch] + d.rgb_bias;
-        c = rgb_act(d.rgb_act, z) * (1.f + 2.f * d.rgb_padding) - d.rgb_padding;
+        c = (rgb_act(d.rgb_act, z) * (1.f + 2.f * d.rgb_padding) - d.rgb_padding) * st.sc[ch];
       }
       st.z[j][ch] = z;
       st.c[j][ch] = c;
@@ -105,7 +109,8 @@ composite_fwd_kernel(mnrf_composite_desc d, const float* __restrict__ raw_densit
                      const float* __restrict__ raw_rgb, const float* __restrict__ density_noise,
                      const float* __restrict__ sdist, const float* __restrict__ directions,
                      const float* __restrict__ near, const float* __restrict__ far,
-                     const float* __restrict__ bg_rgb, float* __restrict__ weights,
+                     const float* __restrict__ bg_rgb, const float* __restrict__ rgb_scale,
+                     float* __restrict__ weights,
                      float* __restrict__ rgb_out, float* __restrict__ density_out,
                      float* __restrict__ rgb_samples, float* __restrict__ acc_out,
                      float* __restrict__ dist_out) {
@@ -119,7 +124,7 @@ composite_fwd_kernel(mnrf_composite_desc d, const float* __restrict__ raw_densit
     const float dx = directions[ray * 3], dy = directions[ray * 3 + 1], dz = directions[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     RayState<CH> st;
-    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, tds, dnorm, st);
+    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, rgb_scale, tds, dnorm, st);
     float px[3] = {0.f, 0.f, 0.f};
     float elog = 0.f;
 #pragma unroll
@@ -194,11 +199,12 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
                      const float* __restrict__ raw_rgb, const float* __restrict__ density_noise,
                      const float* __restrict__ sdist, const float* __restrict__ directions,
                      const float* __restrict__ near, const float* __restrict__ far,
-                     const float* __restrict__ bg_rgb, const float* __restrict__ target_rgb,
+                     const float* __restrict__ bg_rgb, const float* __restrict__ rgb_scale,
+                     const float* __restrict__ target_rgb,
                      const float* __restrict__ lossmult, const float* __restrict__ inv_denom_p,
                      const float* __restrict__ sdist_fine, const float* __restrict__ weights_fine,
                      float* __restrict__ d_raw_density, float* __restrict__ d_raw_rgb,
-                     float* __restrict__ stats) {
+                     float* __restrict__ d_rgb_scale, float* __restrict__ stats) {
   extern __shared__ float smem[];
   const mnrf_composite_desc& d = L.c;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -217,7 +223,7 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
     const float dx = directions[ray * 3], dy = directions[ray * 3 + 1], dz = directions[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     RayState<CH> st;
-    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, tds, dnorm, st);
+    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, rgb_scale, tds, dnorm, st);
 
     // ---- pixel and data loss ------------------------------------------------------------
     float px[3] = {0.f, 0.f, 0.f};
@@ -227,11 +233,12 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
       for (int ch = 0; ch < 3; ++ch) px[ch] += st.w[j] * st.c[j][ch];
     const float bg_w = fmaxf(0.f, 1.f - st.acc);
     const float bg_on = (1.f - st.acc) > 0.f ? 1.f : 0.f;
-    float dpx[3], bgc[3];
+    float dpx[3], bgc[3], wc[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       bgc[ch] = bg_rgb ? bg_rgb[ray * 3 + ch] : d.bg_const;
-      float v = warp_sum(px[ch]) + bg_w * bgc[ch];
+      wc[ch] = warp_sum(px[ch]);                      // sum_s w_s c_s (scaled colour)
+      float v = wc[ch] + bg_w * bgc[ch];
       float tgt = target_rgb[ray * 3 + ch];
       float lm = lossmult[L.lossmult_channels == 3 ? ray * 3 + ch : ray];
       float resid = v - tgt;
@@ -253,6 +260,8 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
       if (lane == 0) {
         st_data += L.data_mult * lm * lv * inv_denom;
         st_mse += lm * resid * resid * inv_denom;
+        // d pixel / d scale = sum_s w_s c_unscaled_s = (sum_s w_s c_s) / scale
+        if (d_rgb_scale) d_rgb_scale[ray * 3 + ch] = st.sc[ch] != 0.f ? dpx[ch] * wc[ch] / st.sc[ch] : 0.f;
       }
     }
 
@@ -375,8 +384,8 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch)
             d_raw_rgb[((size_t)ray * S + s) * 3 + ch] =
-                dpx[ch] * st.w[j] * (1.f + 2.f * d.rgb_padding) * rgb_act_grad(d.rgb_act, st.z[j][ch]) *
-                d.rgb_premult;
+                dpx[ch] * st.w[j] * st.sc[ch] * (1.f + 2.f * d.rgb_padding) *
+                rgb_act_grad(d.rgb_act, st.z[j][ch]) * d.rgb_premult;
         }
       }
       after += g[j] * st.w[j];
@@ -404,9 +413,9 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
 extern "C" int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw_density,
                                   const float* raw_rgb, const float* density_noise,
                                   const float* sdist, const float* directions, const float* near,
-                                  const float* far, const float* bg_rgb, float* weights,
-                                  float* rgb_out, float* density_out, float* rgb_samples,
-                                  float* acc, float* dist, mnrf_stream stream) {
+                                  const float* far, const float* bg_rgb, const float* rgb_scale,
+                                  float* weights, float* rgb_out, float* density_out,
+                                  float* rgb_samples, float* acc, float* dist, mnrf_stream stream) {
   using namespace mnrf;
   MNRF_CHECK(d && raw_density && sdist && directions && near && far && weights && rgb_out,
              "mnrf_composite_fwd: null pointer");
@@ -419,8 +428,8 @@ extern "C" int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw
   int maxb = mnrf_num_sms() * 16;
   if (blocks > maxb) blocks = maxb;
   MNRF_DISPATCH_CH(d->num_samples, (composite_fwd_kernel<CH><<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
-      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, weights, rgb_out,
-      density_out, rgb_samples, acc, dist)));
+      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, rgb_scale, weights,
+      rgb_out, density_out, rgb_samples, acc, dist)));
   MNRF_LAUNCH_CHECK();
   return 0;
 }
@@ -428,12 +437,12 @@ extern "C" int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw
 extern "C" int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_density,
                                   const float* raw_rgb, const float* density_noise,
                                   const float* sdist, const float* directions, const float* near,
-                                  const float* far, const float* bg_rgb, const float* weights,
-                                  const float* rgb_out, const float* target_rgb,
+                                  const float* far, const float* bg_rgb, const float* rgb_scale,
+                                  const float* weights, const float* rgb_out, const float* target_rgb,
                                   const float* lossmult, const float* inv_denom,
                                   const float* sdist_fine, const float* weights_fine,
-                                  float* d_raw_density, float* d_raw_rgb, float* stats,
-                                  mnrf_stream stream) {
+                                  float* d_raw_density, float* d_raw_rgb, float* d_rgb_scale,
+                                  float* stats, mnrf_stream stream) {
   using namespace mnrf;
   (void)weights; (void)rgb_out;   // recomputed in-kernel (bit-identical code path)
   MNRF_CHECK(d && raw_density && sdist && directions && near && far && target_rgb && lossmult &&
@@ -451,8 +460,8 @@ extern "C" int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_dens
   int maxb = mnrf_num_sms() * 16;
   if (blocks > maxb) blocks = maxb;
   MNRF_DISPATCH_CH(d->c.num_samples, (composite_bwd_kernel<CH><<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
-      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, target_rgb, lossmult,
-      inv_denom, sdist_fine, weights_fine, d_raw_density, d_raw_rgb, stats)));
+      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, rgb_scale, target_rgb,
+      lossmult, inv_denom, sdist_fine, weights_fine, d_raw_density, d_raw_rgb, d_rgb_scale, stats)));
   MNRF_LAUNCH_CHECK();
   return 0;
 }

@@ -81,8 +81,8 @@ _SIGNATURES = {
     'mnrf_head_bwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P,
                                 C.c_int64, C.c_int32, _P, _P, _P, _P]),
     'mnrf_colsum': (C.c_int, [C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
-    'mnrf_composite_fwd': (C.c_int, [C.POINTER(CompositeDesc)] + [_P] * 15),
-    'mnrf_composite_bwd': (C.c_int, [C.POINTER(LossDesc)] + [_P] * 19),
+    'mnrf_composite_fwd': (C.c_int, [C.POINTER(CompositeDesc)] + [_P] * 16),
+    'mnrf_composite_bwd': (C.c_int, [C.POINTER(LossDesc)] + [_P] * 21),
     'mnrf_clip_adam': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 6),
     'mnrf_clip_adam_dyn': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 7),
     'mnrf_pack_weights': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -235,8 +235,6 @@ class Model:
       setattr(self, f.name, getattr(m, f.name))
     if m.num_glo_features > 0:
       raise NotImplementedError('GLO embeddings are not wired into the CUDA path yet')
-    if m.learned_exposure_scaling:
-      raise NotImplementedError('learned_exposure_scaling (RawNeRF) is a later milestone')
     if m.bg_intensity_range[0] != m.bg_intensity_range[1]:
       raise NotImplementedError('random background colours are not wired into the CUDA path yet')
     if m.ray_shape not in L.RAY_SHAPE:
@@ -248,6 +246,10 @@ class Model:
     self.plans = {'NerfMLP_0': MLPPlan(bundle.nerf_mlp, m.use_viewdirs)}
     if not m.single_mlp:
       self.plans['PropMLP_0'] = MLPPlan(bundle.prop_mlp, m.use_viewdirs)
+    # non-MLP top-level parameter modules (flax names), each clipped/updated on its own
+    self.extra_params = {}
+    if m.learned_exposure_scaling:
+      self.extra_params['exposure_scaling_offsets'] = m.num_glo_embeddings * 3   # Embed [N,3], zeros
     self.params: Optional[Params] = None
     self.mlps: Dict[str, MLPDevice] = {}
     self._levels: Dict[Any, LevelState] = {}
@@ -259,7 +261,7 @@ class Model:
 
   def init(self, seed=0, flax_params=None):
     """Creates `variables` (random init like flax, or from a flax-style tree of arrays)."""
-    params = Params(self.plans, self.device, {})
+    params = Params(self.plans, self.device, self.extra_params)
     rng = np.random.default_rng(seed)
     host = np.zeros(params.total, np.float32)
     for mname, plan in self.plans.items():
@@ -278,6 +280,11 @@ class Model:
         Wp[rows] = kern
         host[o + s.w_off:o + s.w_off + Wp.size] = Wp.reshape(-1)
         host[o + s.b_off:o + s.b_off + s.out_dim] = bias
+    if flax_params is not None:
+      for name in self.extra_params:
+        if name in flax_params:
+          o, n = params.offsets[name]
+          host[o:o + n] = np.asarray(flax_params[name]['embedding'], np.float32).reshape(-1)
     params.flat.copy_(torch.from_numpy(host))
     self.bind(params)
     return params
@@ -297,6 +304,8 @@ class Model:
         Wp = mlp.W(s).detach().cpu().numpy()
         rows = s.row_map if s.row_map is not None else np.arange(s.in_dim)
         out[mname][s.name] = {'kernel': Wp[rows].copy(), 'bias': mlp.b(s).detach().cpu().numpy().copy()}
+    for name in self.extra_params:
+      out[name] = {'embedding': self.params.seg(name).detach().cpu().numpy().reshape(-1, 3).copy()}
     return out
 
   def export_grads_flax(self):
@@ -309,6 +318,8 @@ class Model:
         rows = s.row_map if s.row_map is not None else np.arange(s.in_dim)
         out[mname][s.name] = {'kernel': Wp[rows].copy(),
                               'bias': mlp.b(s, mlp.grads).detach().cpu().numpy().copy()}
+    for name in self.extra_params:
+      out[name] = {'embedding': self.params.seg(name, self.params.grads).detach().cpu().numpy().reshape(-1, 3).copy()}
     return out
 
   # ------------------------------------------------------------------ schedule
@@ -443,6 +454,16 @@ class Model:
     B = rays.origins.shape[0]
     s_near, s_far, sched = self.level_schedule(train_frac)
     dev = self.device
+    # RawNeRF exposure logic (models.py:257-267): one per-ray colour scale for every level
+    rgb_scale = None
+    if getattr(rays, 'exposure_idx', None) is not None:
+      rgb_scale = rays.exposure_values.expand(B, 3)
+      if m.learned_exposure_scaling:
+        eidx = rays.exposure_idx[:, 0].long()
+        mask = (eidx > 0).to(torch.float32)[:, None]
+        off = self.params.seg('exposure_scaling_offsets').view(-1, 3)[eidx]
+        rgb_scale = rgb_scale * (1 + mask * off)
+      rgb_scale = rgb_scale.contiguous()
     sdist_prev = torch.empty(B, 2, device=dev)
     sdist_prev[:, 0] = s_near
     sdist_prev[:, 1] = s_far
@@ -477,8 +498,9 @@ class Model:
       st.comp_cfg = self._comp_cfg(mlp.plan.cfg)
       st.comp = ops.composite_fwd(st.raw_density, st.raw_rgb, st.sdist, rays.directions,
                                   rays.near_flat, rays.far_flat, cfg=st.comp_cfg,
-                                  density_noise=st.noise, want_samples=want_samples,
-                                  want_extras=compute_extras)
+                                  density_noise=st.noise, rgb_scale=rgb_scale if st.raw_rgb is not None else None,
+                                  want_samples=want_samples, want_extras=compute_extras)
+      st.rgb_scale = rgb_scale if st.raw_rgb is not None else None
       sdist_prev, w_prev = st.sdist, st.comp['weights']
       states.append(st)
     return states

@@ -177,7 +177,7 @@ def _cdesc(B, S, *, raydist_fn, opaque_background, density_bias, density_noise, 
 
 
 def composite_fwd(raw_density, raw_rgb, sdist, directions, near, far, *, cfg, density_noise=None,
-                  bg_rgb=None, want_samples=False, want_extras=False):
+                  bg_rgb=None, rgb_scale=None, want_samples=False, want_extras=False):
   """compute_alpha_weights + volumetric_rendering.  cfg: kwargs of _cdesc."""
   lib = L.load()
   B, S = raw_density.shape
@@ -193,15 +193,15 @@ def composite_fwd(raw_density, raw_rgb, sdist, directions, near, far, *, cfg, de
   L.check(lib.mnrf_composite_fwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
                                  L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
                                  L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
-                                 L.ptr(_f32(bg_rgb)), L.ptr(weights), L.ptr(rgb), L.ptr(dens),
-                                 L.ptr(rgbs), L.ptr(acc), L.ptr(dist), L.stream_ptr()))
+                                 L.ptr(_f32(bg_rgb)), L.ptr(_f32(rgb_scale)), L.ptr(weights), L.ptr(rgb),
+                                 L.ptr(dens), L.ptr(rgbs), L.ptr(acc), L.ptr(dist), L.stream_ptr()))
   return dict(weights=weights, rgb=rgb, density=dens, rgb_samples=rgbs, acc=acc, dist=dist)
 
 
 def composite_bwd(raw_density, raw_rgb, sdist, directions, near, far, target_rgb, lossmult,
                   inv_denom, stats, *, cfg, loss_type, charb_padding, data_mult, distortion_mult,
                   interlevel_mult, sdist_fine=None, weights_fine=None, density_noise=None,
-                  bg_rgb=None, d_raw_density=None, d_raw_rgb=None):
+                  bg_rgb=None, rgb_scale=None, d_raw_density=None, d_raw_rgb=None, d_rgb_scale=None):
   lib = L.load()
   B, S = raw_density.shape
   dev = raw_density.device
@@ -217,10 +217,11 @@ def composite_bwd(raw_density, raw_rgb, sdist, directions, near, far, target_rgb
   L.check(lib.mnrf_composite_bwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
                                  L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
                                  L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
-                                 L.ptr(_f32(bg_rgb)), None, None, L.ptr(_f32(target_rgb)),
+                                 L.ptr(_f32(bg_rgb)), L.ptr(_f32(rgb_scale)), None, None,
+                                 L.ptr(_f32(target_rgb)),
                                  L.ptr(_f32(lossmult)), L.ptr(_f32(inv_denom)),
                                  L.ptr(_f32(sdist_fine)), L.ptr(_f32(weights_fine)),
-                                 L.ptr(d_raw_density), L.ptr(d_raw_rgb), L.ptr(stats),
+                                 L.ptr(d_raw_density), L.ptr(d_raw_rgb), L.ptr(d_rgb_scale), L.ptr(stats),
                                  L.stream_ptr()))
   return d_raw_density, d_raw_rgb
 

@@ -115,12 +115,25 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
           interlevel_mult=0.0 if is_fine else config.interlevel_loss_mult,
           sdist_fine=None if is_fine else fine.sdist,
           weights_fine=None if is_fine else fine.comp['weights'],
-          density_noise=st.noise, d_raw_density=st.d_raw_density, d_raw_rgb=st.d_raw_rgb)
+          density_noise=st.noise, rgb_scale=st.rgb_scale, d_raw_density=st.d_raw_density,
+          d_raw_rgb=st.d_raw_rgb, d_rgb_scale=_d_scale_buf(st))
+      if st.rgb_scale is not None and mcfg.learned_exposure_scaling:
+        # d offsets[idx] += [idx > 0] * exposure_values * d_scale   (adjoint of models.py:262-267)
+        eidx = rays.exposure_idx[:, 0].long()
+        g = (eidx > 0).to(torch.float32)[:, None] * rays.exposure_values * st.d_rgb_scale
+        params.seg('exposure_scaling_offsets', params.grads).view(-1, 3).index_add_(0, eidx, g)
       model._mlp_backward(st, model.mlps[st.mname], impl=impl)
+
+  def _d_scale_buf(st):
+    if st.rgb_scale is None:
+      return None
+    if getattr(st, 'd_rgb_scale', None) is None or st.d_rgb_scale.shape[0] != st.B:
+      st.d_rgb_scale = torch.empty(st.B, 3, device=dev)
+    return st.d_rgb_scale
 
   def optim(grad_scale, step, lr, dyn_ptr):
     params = model.params
-    for name in model.plans:
+    for name in list(model.plans) + list(model.extra_params):
       ops.clip_adam(params.seg(name), params.seg(name, params.grads), params.seg(name, params.mu),
                     params.seg(name, params.nu), scratch, step=step, lr=lr,
                     beta1=config.adam_beta1, beta2=config.adam_beta2, eps=config.adam_eps,

@@ -87,6 +87,8 @@ def test_param_counts_known_answers(mods):
   models, _ = mods
   assert models.Model(configs.bundle_360()).num_params() == 9007493
   assert models.Model(configs.bundle_blender_256()).num_params() == 835205
+  raw = models.Model(configs.bundle_llff_raw())
+  assert raw.num_params() + sum(raw.extra_params.values()) == 615740      # generate_tables.ipynb (llff_raw)
 
 
 @pytest.mark.parametrize('which', ['plumbing', 'mini360'])
@@ -231,3 +233,60 @@ def test_cuda_graph_train_step_matches_eager(mods):
   # fp32 atomics make the two runs differ in the last bits only
   rel = float((p0 - p1).norm() / p0.norm())
   assert rel < 2e-3, rel
+
+
+def test_rawnerf_train_step_vs_oracle(mods):
+  """BASELINE config 4 (llff_raw.gin) at reduced size: single MLP for both levels, cylinder rays,
+  safe_exp colours, per-sample jitter, density noise, exposure scaling with learned offsets, Bayer
+  lossmult, rawnerf loss, coarse data loss, value + norm clipping."""
+  models, train_utils = mods
+  from multinerf_b200 import configs, utils
+  bundle = configs.bundle_llff_raw()
+  bundle.model.num_prop_samples = bundle.model.num_nerf_samples = 32
+  bundle.nerf_mlp.net_width, bundle.nerf_mlp.bottleneck_width, bundle.nerf_mlp.net_width_viewdirs = 128, 64, 64
+  bundle.config.grad_max_norm = 0.0
+  bundle.config.grad_max_val = 0.0
+  B, S = 192, 32
+  rng = np.random.default_rng(21)
+  f = np.float32
+  o = np.concatenate([rng.uniform(-1, 1, (B, 2)), -np.ones((B, 1))], -1)
+  d = np.concatenate([rng.uniform(-.5, .5, (B, 2)), 2 * np.ones((B, 1))], -1)
+  v = d / np.linalg.norm(d, axis=-1, keepdims=True)
+  eidx = rng.integers(0, 4, (B, 1)).astype(np.int32)
+  lossmult = np.eye(3, dtype=f)[rng.integers(0, 3, B)]           # Bayer mask: one channel per ray
+  rays = utils.Rays(origins=o.astype(f), directions=d.astype(f), viewdirs=v.astype(f),
+                    radii=rng.uniform(1e-3, 2e-3, (B, 1)).astype(f), imageplane=np.zeros((B, 2), f),
+                    lossmult=lossmult, near=np.zeros((B, 1), f), far=np.ones((B, 1), f),
+                    cam_idx=np.zeros((B, 1), np.int32), exposure_idx=eidx,
+                    exposure_values=(2.0 ** -eidx).astype(f))
+  target = (rng.uniform(0, 1, (B, 3)) ** 2).astype(f)
+  model, variables = models.construct_model(8, rays, bundle)
+  tree = model.export_flax()
+  tree['exposure_scaling_offsets']['embedding'] = rng.normal(size=(1000, 3)).astype(f) * 0.1
+  variables = model.init(flax_params=tree)
+  params0 = torch_tree(model.export_flax())
+  bases = {'nerf': model.plans['NerfMLP_0'].basis, 'prop': model.plans['NerfMLP_0'].basis}
+  rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, S)).astype(f)) for _ in range(2)],
+          'density_noise': [torch.tensor(rng.normal(size=(B, S)).astype(f)) for _ in range(2)]}
+  opt0 = {'count': 0, 'mu': {}, 'nu': {}}
+  new_o, opt_o, stats_o, grads_o = o_train.train_step(params0, opt0, bundle, bases, oracle_rays(rays),
+                                                      torch.tensor(target), 0.3, rand=rand, bf16=True)
+  step_fn = train_utils.create_train_step(model, bundle.config)
+  state = train_utils.TrainState(variables)
+  state, stats, _ = step_fn(rand, state, utils.Batch(rays=rays, rgb=target), None, 0.3)
+  torch.cuda.synchronize()
+  stats.materialize()
+  close(stats['mses'], stats_o['mses'].detach(), atol=2e-3, rtol=3e-2, msg='mses')
+  lo = float(stats_o['loss'].detach())
+  assert abs(stats['loss'] - lo) < 3e-2 * max(1.0, abs(lo)), (stats['loss'], lo)
+  g = model.export_grads_flax()
+  a = torch.tensor(g['exposure_scaling_offsets']['embedding']).double().flatten()
+  b = grads_o[('exposure_scaling_offsets', 'embedding')].double().flatten()
+  assert float((a - b).norm() / b.norm()) < 0.05 and float(b.norm()) > 0, float((a - b).norm() / b.norm())
+  assert float(a.reshape(-1, 3)[0].abs().max()) == 0.0      # index 0 is pinned (mask = idx > 0)
+  for lname in g['NerfMLP_0']:
+    a = torch.tensor(g['NerfMLP_0'][lname]['kernel']).double().flatten()
+    b = grads_o[('NerfMLP_0', lname, 'kernel')].double().flatten()
+    rel = float((a - b).norm() / b.norm().clamp(min=1e-12))
+    cos = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+    assert rel < 0.15 and cos > 0.99, (lname, rel, cos)
