@@ -68,7 +68,8 @@ class MLPPlan:
     self.F = 2 * self.K * self.L
     self.Fpad = _pad64(self.F)
     W = cfg.net_width
-    assert W % 64 == 0, 'net_width must be a multiple of 64'
+    # tensor-core tiling constraints are checked by Model (the table itself is layout-agnostic)
+    self.device_constraints = [('net_width', W)]
     specs: List[DenseSpec] = []
     k = 0
     x_dim, x_pad, x_has_feat = self.F, self.Fpad, False
@@ -97,14 +98,14 @@ class MLPPlan:
       if cfg.bottleneck_width <= 0:
         raise NotImplementedError('bottleneck_width == 0 is not supported (models.py:536-554)')
       bw = cfg.bottleneck_width
-      assert bw % 64 == 0
+      self.device_constraints.append(('bottleneck_width', bw))
       specs.append(DenseSpec(f'Dense_{k}', 'bottleneck', x_dim, x_pad, bw, False, L.ACT_NONE, rm))
       k += 1
       self.dir_dim = 3 + 6 * cfg.deg_view
       vin, vin_pad = bw + self.dir_dim, _pad64(bw + self.dir_dim)
       self.vin_dim, self.vin_pad = vin, vin_pad
       Wv = cfg.net_width_viewdirs
-      assert Wv % 64 == 0
+      self.device_constraints.append(('net_width_viewdirs', Wv))
       v_dim, v_pad, v_has_in = vin, vin_pad, True
       self.view_concat_after = []
       for i in range(cfg.net_depth_viewdirs):
@@ -246,6 +247,10 @@ class Model:
     self.plans = {'NerfMLP_0': MLPPlan(bundle.nerf_mlp, m.use_viewdirs)}
     if not m.single_mlp:
       self.plans['PropMLP_0'] = MLPPlan(bundle.prop_mlp, m.use_viewdirs)
+    for pname, plan in self.plans.items():
+      for field, val in plan.device_constraints:
+        if val % 64 != 0:
+          raise ValueError(f'{pname}.{field} = {val}: the tcgen05 path tiles layer widths in multiples of 64')
     # non-MLP top-level parameter modules (flax names), each clipped/updated on its own
     self.extra_params = {}
     if m.learned_exposure_scaling:

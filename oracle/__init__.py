@@ -12,10 +12,13 @@ Pinning status (see DESIGN.md "Oracle"):
     `tests/test_oracle_*.py`, and (b) golden vectors produced by executing the
     REAL reference source files in this container under a numpy stand-in for
     `jax.numpy` (`tests/golden/make_golden.py`, fixtures in `tests/golden/*.npz`).
-  * `Model.__call__` / `MLP.__call__` / the train step have no test or golden
-    vector in the reference and JAX/Flax cannot be installed here: those are
-    pinned through the same jax->numpy stand-in run of the real `models.py`
-    forward where the stand-in reaches (see make_golden.py), and are otherwise
-    "parity unpinned" (optax.adam / flax initialisers are restated from their
-    published definitions).
+  * `Model.__call__` / `MLP.__call__` (all four BASELINE model families: mip-NeRF 360, blender,
+    RawNeRF, Ref-NeRF) and the loss functions / clip_gradients of the train-step closure are
+    pinned the same way: `tests/golden/make_golden_model.py` runs the reference's REAL
+    `internal/models.py` and `internal/train_utils.py` under jax/flax/gin stand-ins and
+    `tests/test_oracle_model_golden.py` compares `oracle.o_models.model_apply` and
+    `oracle.o_train.*` against those outputs (fp32, 2e-5 / 2e-4).
+  * Still "parity unpinned": XLA's own float rounding, threefry random streams (randomness is an
+    explicit input here), flax initialisers and optax.adam (restated from their published
+    definitions).
 """

@@ -185,7 +185,7 @@ def model_apply(params, bundle, bases, rays, train_frac, compute_extras, rand=No
   nerf_cfg = bundle.nerf_mlp
   prop_cfg = nerf_cfg if mcfg.single_mlp else bundle.prop_mlp
   nerf_tree = params['NerfMLP_0']
-  prop_tree = nerf_tree if mcfg.single_mlp else params['PropMLP_0']
+  prop_tree = nerf_tree if mcfg.single_mlp else params.get('PropMLP_0')   # unused at num_levels == 1
   rand = rand or {}
 
   if mcfg.num_glo_features > 0:
