@@ -95,6 +95,13 @@ int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const float* orig
                 const float* directions, const float* radii, const float* near,
                 const float* far, const float* basis, mnrf_bf16* feat_bf16, float* feat_f32,
                 float* tdist_out, mnrf_stream stream);
+/* Same, plus the tangent features d(feature)/d(mean_x|y|z) as three stacked bf16 blocks
+ * tfeat[dir*B*S + m, ld_tfeat] (input of the forward-mode density-normal chain that replaces
+ * vmap(value_and_grad(predict_density)), models.py:473-492).  Contraction is not supported here. */
+int mnrf_encode_tangent(const mnrf_encode_desc* d, const float* sdist, const float* origins,
+                        const float* directions, const float* radii, const float* near,
+                        const float* far, const float* basis, mnrf_bf16* feat_bf16,
+                        mnrf_bf16* tfeat_bf16, int32_t ld_tfeat, mnrf_stream stream);
 
 /* View-direction positional encoding, coord.pos_enc (coord.py:136-147) with
  * append_identity, broadcast over the S samples of each ray (models.py:550-554) and
@@ -125,6 +132,9 @@ typedef struct {
   int32_t n, k;       /* output columns; reduction length (WGRAD: number of samples R) */
   int64_t lda, ldb, ldc, ldmask;
   int64_t ldmaskbits; /* row pitch of `maskbits` in 32-bit words */
+  int64_t ldadd;      /* row pitch of `addend` */
+  int64_t mask_mod;   /* > 0: mask row = output row mod mask_mod (the 3 stacked tangent streams of the
+                         density-normal chain share the primal's ReLU masks); 0: mask row = output row */
   int32_t impl;       /* 0 = tcgen05 (product path); 1 = SIMT reference kernel (bring-up/tests) */
 } mnrf_gemm_desc;
 
@@ -133,10 +143,12 @@ typedef struct {
  * (16x less mask traffic).  The caller zero-fills nothing: every word of the tile is written.
  * colsum (optional, DGRAD only): colsum[N] += column sums of the output, i.e. the bias gradient
  * of the layer whose activation masks this dgrad; reduced from the epilogue registers (fp32,
- * before the bf16 rounding of the stored output) -- no separate pass over dY. */
+ * before the bf16 rounding of the stored output) -- no separate pass over dY.
+ * addend (optional, DGRAD only): out += addend[M, ldadd] (bf16), added after the mask -- the second
+ * gradient contribution to an input consumed twice (skip connection of the view MLP). */
 int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
               const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-              float* colsum, void* out, mnrf_stream stream);
+              float* colsum, const mnrf_bf16* addend, void* out, mnrf_stream stream);
 
 /* ---- small heads (N <= 4 outputs): density / rgb / predicted normals ---------------------
  * raw[M, n_out] = X[M, K](bf16) * W[n_out, K](bf16) + b, fp32 accumulate; models.py:460,585.
@@ -176,12 +188,16 @@ typedef struct {
   int32_t rgb_act;
   float rgb_premult, rgb_bias, rgb_padding;
   float bg_const;
+  int32_t rgb_mode;         /* 0: colour = act(raw_rgb); 1: diffuse + specular (models.py:588-599):
+                               clip(linear_to_srgb(tint * act(raw_rgb) + sigmoid(raw_diffuse - log 3)), 0, 1),
+                               tint = sigmoid(raw_tint) or 0.5 when raw_tint is NULL */
 } mnrf_composite_desc;
 
 int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw_density,
                        const float* raw_rgb, const float* density_noise, const float* sdist,
                        const float* directions, const float* near, const float* far,
-                       const float* bg_rgb, const float* rgb_scale, float* weights, float* rgb_out,
+                       const float* bg_rgb, const float* rgb_scale, const float* raw_diffuse,
+                       const float* raw_tint, float* weights, float* rgb_out,
                        float* density_out, float* rgb_samples, float* acc, float* dist,
                        mnrf_stream stream);
 
@@ -209,12 +225,56 @@ typedef struct {
 int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_density, const float* raw_rgb,
                        const float* density_noise, const float* sdist, const float* directions,
                        const float* near, const float* far, const float* bg_rgb,
-                       const float* rgb_scale, const float* weights, const float* rgb_out,
+                       const float* rgb_scale, const float* raw_diffuse, const float* raw_tint,
+                       const float* extra_dw /* [B,S] added to dL/dweights, or NULL */,
                        const float* target_rgb,
                        const float* lossmult, const float* inv_denom /* device scalar */,
                        const float* sdist_fine, const float* weights_fine,
                        float* d_raw_density, float* d_raw_rgb, float* d_rgb_scale /* [B,3] or NULL */,
-                       float* stats, mnrf_stream stream);
+                       float* d_raw_diffuse, float* d_raw_tint, float* stats, mnrf_stream stream);
+
+/* ---- Ref-NeRF per-sample stage ---------------------------------------------------------------
+ * Between the spatial trunk and the directional MLP: normals_pred / normals = -l2_normalize(.)
+ * (models.py:488-499, ref_utils.py:40-42), roughness = softplus(raw + bias) (models.py:520-523),
+ * refdirs = reflect(-viewdirs, normals) (ref_utils.py:22-37, models.py:545), the integrated
+ * directional encoding (ref_utils.generate_ide_fn ref_utils.py:98-159; ide_mat [l_max+1, ide_n]
+ * fp32 and ide_ml int32 [2, ide_n] = (m | l) come from multinerf_b200/ref_utils.py) or coord.pos_enc,
+ * and n.v (models.py:560-563).  Writes the bf16 slab [col0, col_end) of the view-MLP input.
+ * raw_grad_density / d_raw_grad_density are direction-major [3, M].
+ * Backward adds train_utils.orientation_loss (:162-178) and predicted_normal_loss (:181-197):
+ * orient_mult / prednorm_mult are the level's multipliers divided by the number of rays;
+ * extra_dw [M] (forward) receives d(loss)/d(weights) of those two terms; stats[4], stats[5] their
+ * values.  After consuming d_slab[:, col0:col_end) (the gradient of the encoding), the backward
+ * overwrites those columns with the 11 head gradients (raw_density, grad_pred x3, raw_diffuse x3,
+ * raw_tint x3, raw_roughness; bf16, zero-padded) so that [bottleneck grad | head grads] is the A
+ * operand of a single dgrad GEMM into the trunk.
+ */
+typedef struct {
+  int64_t M;
+  int32_t num_samples;
+  int32_t use_pred_normals, use_density_normals, use_reflections, use_ide, use_n_dot_v, use_roughness;
+  int32_t deg_view, ide_n;
+  float roughness_bias;
+  int32_t ld, col0, col_end;
+} mnrf_refdir_desc;
+
+int mnrf_refdir_fwd(const mnrf_refdir_desc* d, const float* ide_mat, const int32_t* ide_ml,
+                    const float* grad_pred, const float* raw_rough, const float* raw_grad_density,
+                    const float* viewdirs, float* normals_pred, float* normals, float* roughness,
+                    mnrf_bf16* slab, float orient_mult, float prednorm_mult, int32_t orient_on_pred,
+                    float* extra_dw /* [M] or NULL */, mnrf_stream stream);
+int mnrf_refdir_bwd(const mnrf_refdir_desc* d, const float* ide_mat, const int32_t* ide_ml,
+                    const float* grad_pred, const float* raw_rough, const float* raw_grad_density,
+                    const float* viewdirs, const float* weights, mnrf_bf16* d_slab,
+                    int32_t ld_dslab, float orient_mult, float prednorm_mult, int32_t orient_on_pred,
+                    const float* d_raw_density, const float* d_raw_diffuse, const float* d_raw_tint,
+                    float* d_grad_pred, float* d_raw_rough, float* d_raw_grad_density,
+                    float* stats, mnrf_stream stream);
+/* out[r, n] bf16 = maskbit(r mod mask_mod, n) ? rowv[r] * colv[n] : 0 -- the first dY of the
+ * density-normal (tangent) backward chain. */
+int mnrf_outer_mask(int64_t rows, int32_t n, int64_t mask_mod, const float* rowv, const float* colv,
+                    const uint32_t* maskbits, int64_t ldmaskbits, mnrf_bf16* out, int64_t ldo,
+                    mnrf_stream stream);
 
 /* ---- optimizer ---------------------------------------------------------------------------
  * train_utils.clip_gradients (train_utils.py:200-218: value clip, then global-norm clip with

@@ -103,6 +103,24 @@ __device__ __forceinline__ float safe_sin_fast(float x) {
   return __sinf(r);
 }
 
+// sin and cos of the same reduced argument (the cosine is d/dx safe_sin(x), used by the tangent
+// features of the density-normal chain).
+__device__ __forceinline__ void safe_sincos_fast(float x, float& sn, float& cs) {
+  const float t = 314.159271240234375f;
+  if (!(fabsf(x) < t)) {
+    float k = floorf(__fmul_rn(x, 1.f / t));
+    float r = __fmaf_rn(-k, t, x);
+    if (r < 0.f) r = __fadd_rn(r, t);
+    else if (r >= t) r = __fsub_rn(r, t);
+    x = r;
+  }
+  const float q = rintf(__fmul_rn(x, 0.15915494309189535f));
+  float r = __fmaf_rn(-q, 6.2831854820251465f, x);
+  r = __fmaf_rn(q, 1.7484555e-7f, r);
+  sn = __sinf(r);
+  cs = __cosf(r);
+}
+
 // s_to_t of coord.construct_ray_warps (coord.py:63-99) for one value.
 __device__ __forceinline__ float fwd_raydist(int fn, float x) {
   switch (fn) {

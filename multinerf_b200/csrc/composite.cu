@@ -24,12 +24,36 @@ struct RayState {
   float c[CH][3];   // activated + padded colour, times the per-ray exposure scale
   float z[CH][3];   // premult * raw + bias (argument of the rgb activation)
   float sc[3];      // per-ray rgb scale (RawNeRF exposure, models.py:257-267); 1 if absent
+  float zd[CH][3];  // Ref-NeRF: raw diffuse colour (pre-activation), rgb_mode 1
+  float zt[CH][3];  // Ref-NeRF: raw specular tint (pre-activation), rgb_mode 1
   float acc;        // sum of w
 };
 
 __device__ __forceinline__ float rgb_act(int kind, float z) {
   return kind == MNRF_RGB_SAFE_EXP ? expf(fminf(z, 88.f)) : sigmoid_f(z);
 }
+// image.linear_to_srgb (image.py:48-56) and its derivative
+__device__ __forceinline__ float lin2srgb(float x) {
+  return x <= 0.0031308f ? (323.f / 25.f) * x : (211.f * powf(fmaxf(kEps, x), 5.f / 12.f) - 11.f) / 200.f;
+}
+__device__ __forceinline__ float lin2srgb_grad(float x) {
+  if (x <= 0.0031308f) return 323.f / 25.f;
+  return x > kEps ? (211.f / 200.f) * (5.f / 12.f) * powf(x, -7.f / 12.f) : 0.f;
+}
+constexpr float kLog3 = 1.09861228866810969f;
+
+// colour of one channel: returns c (before the per-ray scale); mode 1 = diffuse + tinted specular
+__device__ __forceinline__ float colour_fwd(const mnrf_composite_desc& d, float z, float zd, float zt,
+                                            bool has_tint) {
+  float a = rgb_act(d.rgb_act, z);
+  if (d.rgb_mode == 1) {
+    float t = has_tint ? sigmoid_f(zt) : 0.5f;
+    float lin = t * a + sigmoid_f(zd - kLog3);
+    a = fminf(fmaxf(lin2srgb(lin), 0.f), 1.f);
+  }
+  return a * (1.f + 2.f * d.rgb_padding) - d.rgb_padding;
+}
+
 __device__ __forceinline__ float rgb_act_grad(int kind, float z) {
   if (kind == MNRF_RGB_SAFE_EXP) return expf(fminf(z, 88.f));
   float s = sigmoid_f(z);
@@ -42,6 +66,8 @@ __device__ __forceinline__ void ray_forward(const mnrf_composite_desc& d, int ra
                                             const float* __restrict__ raw_rgb,
                                             const float* __restrict__ density_noise,
                                             const float* __restrict__ rgb_scale,
+                                            const float* __restrict__ raw_diffuse,
+                                            const float* __restrict__ raw_tint,
                                             const float* tds, float dnorm, RayState<CH>& st) {
   const int S = d.num_samples;
   float local = 0.f;
@@ -64,12 +90,19 @@ __device__ __forceinline__ void ray_forward(const mnrf_composite_desc& d, int ra
     if (s < S - 1) local += a;   // the last a never enters a prefix that is used
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      float z = 0.f, c = 0.f;
+      float z = 0.f, c = 0.f, zd = 0.f, zt = 0.f;
       if (raw_rgb && ok) {
-        z = d.rgb_premult * raw_rgb[((size_t)ray * S + s) * 3 + ch] + d.rgb_bias;
-        c = (rgb_act(d.rgb_act, z) * (1.f + 2.f * d.rgb_padding) - d.rgb_padding) * st.sc[ch];
+        const size_t ci = ((size_t)ray * S + s) * 3 + ch;
+        z = d.rgb_premult * raw_rgb[ci] + d.rgb_bias;
+        if (d.rgb_mode == 1) {
+          zd = raw_diffuse[ci];
+          if (raw_tint) zt = raw_tint[ci];
+        }
+        c = colour_fwd(d, z, zd, zt, raw_tint != nullptr) * st.sc[ch];
       }
       st.z[j][ch] = z;
+      st.zd[j][ch] = zd;
+      st.zt[j][ch] = zt;
       st.c[j][ch] = c;
     }
   }
@@ -110,6 +143,7 @@ composite_fwd_kernel(mnrf_composite_desc d, const float* __restrict__ raw_densit
                      const float* __restrict__ sdist, const float* __restrict__ directions,
                      const float* __restrict__ near, const float* __restrict__ far,
                      const float* __restrict__ bg_rgb, const float* __restrict__ rgb_scale,
+                     const float* __restrict__ raw_diffuse, const float* __restrict__ raw_tint,
                      float* __restrict__ weights,
                      float* __restrict__ rgb_out, float* __restrict__ density_out,
                      float* __restrict__ rgb_samples, float* __restrict__ acc_out,
@@ -124,7 +158,8 @@ composite_fwd_kernel(mnrf_composite_desc d, const float* __restrict__ raw_densit
     const float dx = directions[ray * 3], dy = directions[ray * 3 + 1], dz = directions[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     RayState<CH> st;
-    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, rgb_scale, tds, dnorm, st);
+    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, rgb_scale, raw_diffuse, raw_tint, tds,
+                    dnorm, st);
     float px[3] = {0.f, 0.f, 0.f};
     float elog = 0.f;
 #pragma unroll
@@ -200,11 +235,13 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
                      const float* __restrict__ sdist, const float* __restrict__ directions,
                      const float* __restrict__ near, const float* __restrict__ far,
                      const float* __restrict__ bg_rgb, const float* __restrict__ rgb_scale,
-                     const float* __restrict__ target_rgb,
+                     const float* __restrict__ raw_diffuse, const float* __restrict__ raw_tint,
+                     const float* __restrict__ extra_dw, const float* __restrict__ target_rgb,
                      const float* __restrict__ lossmult, const float* __restrict__ inv_denom_p,
                      const float* __restrict__ sdist_fine, const float* __restrict__ weights_fine,
                      float* __restrict__ d_raw_density, float* __restrict__ d_raw_rgb,
-                     float* __restrict__ d_rgb_scale, float* __restrict__ stats) {
+                     float* __restrict__ d_rgb_scale, float* __restrict__ d_raw_diffuse,
+                     float* __restrict__ d_raw_tint, float* __restrict__ stats) {
   extern __shared__ float smem[];
   const mnrf_composite_desc& d = L.c;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -223,7 +260,8 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
     const float dx = directions[ray * 3], dy = directions[ray * 3 + 1], dz = directions[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     RayState<CH> st;
-    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, rgb_scale, tds, dnorm, st);
+    ray_forward<CH>(d, ray, lane, raw_density, raw_rgb, density_noise, rgb_scale, raw_diffuse, raw_tint, tds,
+                    dnorm, st);
 
     // ---- pixel and data loss ------------------------------------------------------------
     float px[3] = {0.f, 0.f, 0.f};
@@ -272,6 +310,10 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
       g[j] = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) g[j] += dpx[ch] * (st.c[j][ch] - bg_on * bgc[ch]);
+      if (extra_dw) {        // orientation / predicted-normal losses (train_utils.py:162-197)
+        int s = lane * CH + j;
+        if (s < S) g[j] += extra_dw[(size_t)ray * S + s];
+      }
     }
 
     // ---- distortion loss (final level) in normalised s-space ---------------------------
@@ -382,10 +424,25 @@ composite_bwd_kernel(mnrf_loss_desc L, const float* __restrict__ raw_density,
         d_raw_density[(size_t)ray * S + s] = dd;
         if (d_raw_rgb) {
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch)
-            d_raw_rgb[((size_t)ray * S + s) * 3 + ch] =
-                dpx[ch] * st.w[j] * st.sc[ch] * (1.f + 2.f * d.rgb_padding) *
-                rgb_act_grad(d.rgb_act, st.z[j][ch]) * d.rgb_premult;
+          for (int ch = 0; ch < 3; ++ch) {
+            const size_t ci = ((size_t)ray * S + s) * 3 + ch;
+            // dL/d(colour before padding and scale)
+            const float gc = dpx[ch] * st.w[j] * st.sc[ch] * (1.f + 2.f * d.rgb_padding);
+            const float da = rgb_act_grad(d.rgb_act, st.z[j][ch]) * d.rgb_premult;
+            if (d.rgb_mode == 1) {
+              const float a = rgb_act(d.rgb_act, st.z[j][ch]);
+              const float t = raw_tint ? sigmoid_f(st.zt[j][ch]) : 0.5f;
+              const float dl = sigmoid_f(st.zd[j][ch] - kLog3);
+              const float lin = t * a + dl;
+              const float sr = lin2srgb(lin);
+              const float glin = (sr > 0.f && sr < 1.f) ? gc * lin2srgb_grad(lin) : 0.f;
+              d_raw_rgb[ci] = glin * t * da;
+              d_raw_diffuse[ci] = glin * dl * (1.f - dl);
+              if (d_raw_tint) d_raw_tint[ci] = raw_tint ? glin * a * t * (1.f - t) : 0.f;
+            } else {
+              d_raw_rgb[ci] = gc * da;
+            }
+          }
         }
       }
       after += g[j] * st.w[j];
@@ -414,6 +471,7 @@ extern "C" int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw
                                   const float* raw_rgb, const float* density_noise,
                                   const float* sdist, const float* directions, const float* near,
                                   const float* far, const float* bg_rgb, const float* rgb_scale,
+                                  const float* raw_diffuse, const float* raw_tint,
                                   float* weights, float* rgb_out, float* density_out,
                                   float* rgb_samples, float* acc, float* dist, mnrf_stream stream) {
   using namespace mnrf;
@@ -421,6 +479,7 @@ extern "C" int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw
              "mnrf_composite_fwd: null pointer");
   MNRF_CHECK(d->num_samples >= 1 && d->num_samples <= 256, "mnrf_composite_fwd: num_samples %d > 256",
              d->num_samples);
+  MNRF_CHECK(d->rgb_mode == 0 || (raw_rgb && raw_diffuse), "mnrf_composite_fwd: rgb_mode 1 needs raw_diffuse");
   if (d->num_rays == 0) return 0;
   const int nw = 4;
   size_t smem = (size_t)nw * (2 * d->num_samples + 4) * sizeof(float);
@@ -428,8 +487,8 @@ extern "C" int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw
   int maxb = mnrf_num_sms() * 16;
   if (blocks > maxb) blocks = maxb;
   MNRF_DISPATCH_CH(d->num_samples, (composite_fwd_kernel<CH><<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
-      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, rgb_scale, weights,
-      rgb_out, density_out, rgb_samples, acc, dist)));
+      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, rgb_scale, raw_diffuse,
+      raw_tint, weights, rgb_out, density_out, rgb_samples, acc, dist)));
   MNRF_LAUNCH_CHECK();
   return 0;
 }
@@ -438,13 +497,16 @@ extern "C" int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_dens
                                   const float* raw_rgb, const float* density_noise,
                                   const float* sdist, const float* directions, const float* near,
                                   const float* far, const float* bg_rgb, const float* rgb_scale,
-                                  const float* weights, const float* rgb_out, const float* target_rgb,
+                                  const float* raw_diffuse, const float* raw_tint, const float* extra_dw,
+                                  const float* target_rgb,
                                   const float* lossmult, const float* inv_denom,
                                   const float* sdist_fine, const float* weights_fine,
                                   float* d_raw_density, float* d_raw_rgb, float* d_rgb_scale,
-                                  float* stats, mnrf_stream stream) {
+                                  float* d_raw_diffuse, float* d_raw_tint, float* stats,
+                                  mnrf_stream stream) {
   using namespace mnrf;
-  (void)weights; (void)rgb_out;   // recomputed in-kernel (bit-identical code path)
+  MNRF_CHECK(d->c.rgb_mode == 0 || (raw_rgb && raw_diffuse && d_raw_diffuse && (!raw_tint || d_raw_tint)),
+             "mnrf_composite_bwd: rgb_mode 1 needs raw_diffuse / d_raw_diffuse (and d_raw_tint with raw_tint)");
   MNRF_CHECK(d && raw_density && sdist && directions && near && far && target_rgb && lossmult &&
              inv_denom && d_raw_density && stats, "mnrf_composite_bwd: null pointer");
   MNRF_CHECK(d->c.num_samples >= 1 && d->c.num_samples <= 256, "mnrf_composite_bwd: num_samples %d > 256",
@@ -460,8 +522,9 @@ extern "C" int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_dens
   int maxb = mnrf_num_sms() * 16;
   if (blocks > maxb) blocks = maxb;
   MNRF_DISPATCH_CH(d->c.num_samples, (composite_bwd_kernel<CH><<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
-      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, rgb_scale, target_rgb,
-      lossmult, inv_denom, sdist_fine, weights_fine, d_raw_density, d_raw_rgb, d_rgb_scale, stats)));
+      *d, raw_density, raw_rgb, density_noise, sdist, directions, near, far, bg_rgb, rgb_scale, raw_diffuse,
+      raw_tint, extra_dw, target_rgb, lossmult, inv_denom, sdist_fine, weights_fine, d_raw_density, d_raw_rgb,
+      d_rgb_scale, d_raw_diffuse, d_raw_tint, stats)));
   MNRF_LAUNCH_CHECK();
   return 0;
 }

@@ -88,7 +88,7 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
               const float* __restrict__ radii, const float* __restrict__ near,
               const float* __restrict__ far, const float* __restrict__ basis,
               __nv_bfloat16* __restrict__ feat, float* __restrict__ feat_f32,
-              float* __restrict__ tdist_out) {
+              float* __restrict__ tdist_out, __nv_bfloat16* __restrict__ tfeat, int ld_tfeat) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int S = d.num_samples, K = d.basis_k, L = d.max_deg - d.min_deg, KL = K * L;
@@ -101,11 +101,15 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
   float* lm = gs + S * kGaussStride;
   float* lv = lm + K;
   unsigned char* rows = smem_raw + (((size_t)(3 * K + nw * per_warp_f) * 4 + 15) / 16) * 16;
-  __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(rows + (size_t)wib * row_bytes);
+  const int rows_per_warp = tfeat ? 4 : 1;        // feature row + three tangent rows
+  __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(rows + (size_t)wib * rows_per_warp * row_bytes);
+  __nv_bfloat16* trow = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(row) + row_bytes);
+  const int trow_elems = row_bytes / 2;
+  const size_t M_total = (size_t)d.num_rays * d.num_samples;
 
   for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) sb[i] = basis[i];
   __syncthreads();
-  for (int i = lane; i < d.feat_cols; i += 32) row[i] = __float2bfloat16(0.f);
+  for (int i = lane; i < d.feat_cols * rows_per_warp; i += 32) row[i + (i / d.feat_cols) * (trow_elems - d.feat_cols)] = __float2bfloat16(0.f);
   // (l, k) of feature f = l*K + k advance by 32 features per iteration without integer division
   const int q32 = 32 / K, r32 = 32 - q32 * K;
   const int l_first = lane / K, k_first = lane - l_first * K;
@@ -154,8 +158,24 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
         float y = lm[k] * sc;
         float v = lv[k] * (sc * sc);
         float e = __expf(-0.5f * v);
-        float fs = e * safe_sin_fast(y);
-        float fc = e * safe_sin_fast(y + 1.57079637050628662109375f);
+        float fs, fc;
+        if (tfeat) {
+          // d/d mean_dir of e * safe_sin(lm * sc) = e * cos(reduced arg) * sc * basis[k][dir]
+          float s0, c0, s1, c1;
+          safe_sincos_fast(y, s0, c0);
+          safe_sincos_fast(y + 1.57079637050628662109375f, s1, c1);
+          fs = e * s0;
+          fc = e * s1;
+#pragma unroll
+          for (int dir = 0; dir < 3; ++dir) {
+            const float bk = sb[k * 3 + dir] * sc * e;
+            trow[dir * trow_elems + f] = __float2bfloat16(c0 * bk);
+            trow[dir * trow_elems + KL + f] = __float2bfloat16(c1 * bk);
+          }
+        } else {
+          fs = e * safe_sin_fast(y);
+          fc = e * safe_sin_fast(y + 1.57079637050628662109375f);
+        }
         row[f] = __float2bfloat16(fs);
         row[KL + f] = __float2bfloat16(fc);
         if (feat_f32) {
@@ -170,6 +190,14 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
       const uint4* src = reinterpret_cast<const uint4*>(row);
       uint4* dst = reinterpret_cast<uint4*>(feat + m * (size_t)d.ld_feat);
       for (int c = lane; c < row_bytes / 16; c += 32) dst[c] = src[c];
+      if (tfeat) {
+#pragma unroll
+        for (int dir = 0; dir < 3; ++dir) {
+          const uint4* ts = reinterpret_cast<const uint4*>(trow + dir * trow_elems);
+          uint4* td = reinterpret_cast<uint4*>(tfeat + ((size_t)dir * M_total + m) * (size_t)ld_tfeat);
+          for (int c = lane; c < row_bytes / 16; c += 32) td[c] = ts[c];
+        }
+      }
       __syncwarp();
     }
   }
@@ -202,11 +230,17 @@ __global__ void viewdir_enc_kernel(int num_rays, int S, int deg, const float* __
 
 }  // namespace mnrf
 
-extern "C" int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const float* origins,
-                           const float* directions, const float* radii, const float* near,
-                           const float* far, const float* basis, mnrf_bf16* feat_bf16,
-                           float* feat_f32, float* tdist_out, mnrf_stream stream) {
+static int encode_impl(const mnrf_encode_desc* d, const float* sdist, const float* origins,
+                       const float* directions, const float* radii, const float* near,
+                       const float* far, const float* basis, mnrf_bf16* feat_bf16,
+                       float* feat_f32, float* tdist_out, mnrf_bf16* tfeat, int ld_tfeat,
+                       mnrf_stream stream) {
   using namespace mnrf;
+  if (tfeat) {
+    MNRF_CHECK(!d->warp_contract, "mnrf_encode_tangent: density normals with a contraction warp are not supported");
+    MNRF_CHECK(ld_tfeat >= d->feat_cols && ld_tfeat % 8 == 0 && ((uintptr_t)tfeat % 16) == 0,
+               "mnrf_encode_tangent: tangent rows must be 16-byte aligned");
+  }
   MNRF_CHECK(d && sdist && origins && directions && radii && near && far && basis && feat_bf16,
              "mnrf_encode: null pointer");
   MNRF_CHECK(d->ray_shape == MNRF_RAY_CONE || d->ray_shape == MNRF_RAY_CYLINDER,
@@ -221,7 +255,7 @@ extern "C" int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const 
   const int row_bytes = ((d->feat_cols * 2 + 15) / 16) * 16;
   size_t smem = (((size_t)(3 * d->basis_k + nw * ((d->num_samples + 1) + d->num_samples * kGaussStride +
                                                    2 * d->basis_k)) * 4 + 15) / 16) * 16 +
-                (size_t)nw * row_bytes;
+                (size_t)nw * row_bytes * (tfeat ? 4 : 1);
   MNRF_CHECK(smem <= 200 * 1024, "mnrf_encode: shared memory %zu too large", smem);
   MNRF_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks = ceil_div(d->num_rays, nw);
@@ -229,9 +263,28 @@ extern "C" int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const 
   if (blocks > max_blocks) blocks = max_blocks;
   encode_kernel<<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
       *d, sdist, origins, directions, radii, near, far, basis,
-      reinterpret_cast<__nv_bfloat16*>(feat_bf16), feat_f32, tdist_out);
+      reinterpret_cast<__nv_bfloat16*>(feat_bf16), feat_f32, tdist_out,
+      reinterpret_cast<__nv_bfloat16*>(tfeat), ld_tfeat);
   MNRF_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mnrf_encode(const mnrf_encode_desc* d, const float* sdist, const float* origins,
+                           const float* directions, const float* radii, const float* near,
+                           const float* far, const float* basis, mnrf_bf16* feat_bf16,
+                           float* feat_f32, float* tdist_out, mnrf_stream stream) {
+  return encode_impl(d, sdist, origins, directions, radii, near, far, basis, feat_bf16, feat_f32, tdist_out,
+                     nullptr, 0, stream);
+}
+
+extern "C" int mnrf_encode_tangent(const mnrf_encode_desc* d, const float* sdist, const float* origins,
+                                   const float* directions, const float* radii, const float* near,
+                                   const float* far, const float* basis, mnrf_bf16* feat_bf16,
+                                   mnrf_bf16* tfeat_bf16, int32_t ld_tfeat, mnrf_stream stream) {
+  mnrf::set_error("");
+  if (!tfeat_bf16) { mnrf::set_error("mnrf_encode_tangent: null tangent buffer"); return 1; }
+  return encode_impl(d, sdist, origins, directions, radii, near, far, basis, feat_bf16, nullptr, nullptr,
+                     tfeat_bf16, ld_tfeat, stream);
 }
 
 extern "C" int mnrf_viewdir_enc(int32_t num_rays, int32_t num_samples, int32_t deg,

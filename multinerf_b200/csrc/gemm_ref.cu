@@ -8,7 +8,7 @@ namespace mnrf {
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                    const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                   float* colsum, void* out, cudaStream_t stream);
+                   float* colsum, const mnrf_bf16* addend, void* out, cudaStream_t stream);
 
 __device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
@@ -17,7 +17,7 @@ __global__ void gemm_ref_nt_kernel(mnrf_gemm_desc d, const __nv_bfloat16* __rest
                                    const __nv_bfloat16* __restrict__ b, const float* __restrict__ bias,
                                    const float* __restrict__ rowv, const float* __restrict__ colv,
                                    const __nv_bfloat16* __restrict__ mask, uint32_t* __restrict__ maskbits,
-                                   __nv_bfloat16* __restrict__ out) {
+                                   const __nv_bfloat16* __restrict__ addend, __nv_bfloat16* __restrict__ out) {
   __shared__ float sa[16][17], sb[16][17];
   const int64_t m = (int64_t)blockIdx.y * 16 + threadIdx.y;
   const int n = blockIdx.x * 16 + threadIdx.x;
@@ -42,10 +42,12 @@ __global__ void gemm_ref_nt_kernel(mnrf_gemm_desc d, const __nv_bfloat16* __rest
   } else {
     if (rowv) acc += rowv[m] * colv[n];
     if (maskbits) {
-      if (!((maskbits[m * d.ldmaskbits + (n >> 5)] >> (n & 31)) & 1u)) acc = 0.f;
+      const int64_t mrow = d.mask_mod > 0 ? m % d.mask_mod : m;
+      if (!((maskbits[mrow * d.ldmaskbits + (n >> 5)] >> (n & 31)) & 1u)) acc = 0.f;
     } else if (mask && !(ldbf(mask + m * d.ldmask + n) > 0.f)) {
       acc = 0.f;
     }
+    if (addend) acc += ldbf(addend + m * d.ldadd + n);
   }
   out[m * d.ldc + n] = __float2bfloat16(acc);
 }
@@ -76,7 +78,7 @@ __global__ void gemm_ref_tn_kernel(mnrf_gemm_desc d, const __nv_bfloat16* __rest
 
 extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                          const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                         float* colsum, void* out, mnrf_stream stream) {
+                         float* colsum, const mnrf_bf16* addend, void* out, mnrf_stream stream) {
   using namespace mnrf;
   MNRF_CHECK(d && a && b && out, "mnrf_gemm: null pointer");
   MNRF_CHECK(d->mode >= 0 && d->mode <= 2, "mnrf_gemm: unknown mode %d", d->mode);
@@ -84,7 +86,8 @@ extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf
   if (d->m == 0 || d->n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (colsum) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD, "mnrf_gemm: colsum is a DGRAD output");
-  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, maskbits, colsum, out, s);
+  if (addend) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD, "mnrf_gemm: addend is a DGRAD input");
+  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, maskbits, colsum, addend, out, s);
   dim3 block(16, 16);
   if (d->mode != MNRF_GEMM_WGRAD) {
     dim3 grid((d->n + 15) / 16, (unsigned)((d->m + 15) / 16));
@@ -95,6 +98,7 @@ extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf
     gemm_ref_nt_kernel<<<grid, block, 0, s>>>(*d, reinterpret_cast<const __nv_bfloat16*>(a),
                                                reinterpret_cast<const __nv_bfloat16*>(b), bias, rowv, colv,
                                                reinterpret_cast<const __nv_bfloat16*>(mask), maskbits,
+                                               reinterpret_cast<const __nv_bfloat16*>(addend),
                                                reinterpret_cast<__nv_bfloat16*>(out));
     MNRF_LAUNCH_CHECK();
     if (colsum) {   // reference path: sum the (bf16-rounded) output in a second pass

@@ -184,6 +184,9 @@ struct GemmParams {
   const __nv_bfloat16* mask;
   uint32_t* maskbits;         // FWD+ReLU: written (1 bit per output, word = 32 columns); DGRAD: read
   int64_t ldmaskbits;         // in 32-bit words
+  int64_t mask_mod;           // > 0: mask row = output row mod mask_mod
+  const __nv_bfloat16* addend;  // DGRAD: out += addend[M, ldadd] (second contribution to a shared input)
+  int64_t ldadd;
   int use_tma_store;
   float* colsum;              // DGRAD: colsum[N] += column sums of the output (bias gradient of the
                               // layer that produced the masking activation), from the epilogue registers
@@ -329,7 +332,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (MODE == MNRF_GEMM_DGRAD) {
         if (p.rowv && row_ok) rv = p.rowv[row];
         if (p.maskbits && row_ok) {
-          const uint32_t* mp = p.maskbits + row * p.ldmaskbits + (ncol0 >> 5);
+          const int64_t mrow = p.mask_mod > 0 ? row % p.mask_mod : row;
+          const uint32_t* mp = p.maskbits + mrow * p.ldmaskbits + (ncol0 >> 5);
 #pragma unroll
           for (int w = 0; w < MAX_BLOCK_N / 32; ++w)
             if (w * 32 < p.block_n) mbits[w] = mp[w];
@@ -416,6 +420,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   if (!(bf16_hi(mm[e]) > 0.f)) v[g * 8 + 2 * e + 1] = 0.f;
                 }
               }
+            }
+          }
+        }
+        if (MODE == MNRF_GEMM_DGRAD && p.addend && row_ok) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.addend + row * p.ldadd + col);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c0 + g * 8 < p.block_n) {
+              uint4 av = ap[g];
+              uint32_t aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { v[g * 8 + 2 * e] += bf16_lo(aa[e]); v[g * 8 + 2 * e + 1] += bf16_hi(aa[e]); }
             }
           }
         }
@@ -541,7 +557,7 @@ static int pick_block_n(int n) {
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                    const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                   float* colsum, void* out, cudaStream_t stream) {
+                   float* colsum, const mnrf_bf16* addend, void* out, cudaStream_t stream) {
   MNRF_CHECK(d->k % BLOCK_K == 0, "mnrf_gemm(tc): reduction length %d must be a multiple of %d", d->k, BLOCK_K);
   MNRF_CHECK(d->lda % 8 == 0 && d->ldb % 8 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0,
              "mnrf_gemm(tc): operands must be 16-byte aligned with ld %% 8 == 0");
@@ -560,6 +576,11 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   p.out = out;
   p.maskbits = maskbits;
   p.ldmaskbits = d->ldmaskbits;
+  p.mask_mod = d->mask_mod;
+  p.addend = reinterpret_cast<const __nv_bfloat16*>(addend);
+  p.ldadd = d->ldadd;
+  if (addend) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD && d->ldadd % 8 == 0 && ((uintptr_t)addend % 16) == 0,
+                         "mnrf_gemm(tc): addend is a DGRAD input with 16-byte aligned rows");
   p.colsum = colsum;
   if (colsum) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD && p.block_n % 32 == 0,
                          "mnrf_gemm(tc): colsum is a DGRAD output and needs N %% 32 == 0");

@@ -34,14 +34,17 @@ class EncodeDesc(C.Structure):
 class GemmDesc(C.Structure):
   _fields_ = [('mode', C.c_int32), ('act', C.c_int32), ('m', C.c_int64), ('n', C.c_int32),
               ('k', C.c_int32), ('lda', C.c_int64), ('ldb', C.c_int64), ('ldc', C.c_int64),
-              ('ldmask', C.c_int64), ('ldmaskbits', C.c_int64), ('impl', C.c_int32)]
+              ('ldmask', C.c_int64), ('ldmaskbits', C.c_int64), ('ldadd', C.c_int64),
+              ('mask_mod', C.c_int64),
+              ('impl', C.c_int32)]
 
 
 class CompositeDesc(C.Structure):
   _fields_ = [('num_rays', C.c_int32), ('num_samples', C.c_int32), ('raydist_fn', C.c_int32),
               ('opaque_background', C.c_int32), ('density_bias', C.c_float),
               ('density_noise', C.c_float), ('rgb_act', C.c_int32), ('rgb_premult', C.c_float),
-              ('rgb_bias', C.c_float), ('rgb_padding', C.c_float), ('bg_const', C.c_float)]
+              ('rgb_bias', C.c_float), ('rgb_padding', C.c_float), ('bg_const', C.c_float),
+              ('rgb_mode', C.c_int32)]
 
 
 class LossDesc(C.Structure):
@@ -49,6 +52,14 @@ class LossDesc(C.Structure):
               ('data_mult', C.c_float), ('distortion_mult', C.c_float),
               ('interlevel_mult', C.c_float), ('num_samples_fine', C.c_int32),
               ('lossmult_channels', C.c_int32)]
+
+
+class RefdirDesc(C.Structure):
+  _fields_ = [('M', C.c_int64), ('num_samples', C.c_int32), ('use_pred_normals', C.c_int32),
+              ('use_density_normals', C.c_int32), ('use_reflections', C.c_int32), ('use_ide', C.c_int32),
+              ('use_n_dot_v', C.c_int32), ('use_roughness', C.c_int32), ('deg_view', C.c_int32),
+              ('ide_n', C.c_int32), ('roughness_bias', C.c_float), ('ld', C.c_int32), ('col0', C.c_int32),
+              ('col_end', C.c_int32)]
 
 
 class AdamDesc(C.Structure):
@@ -76,13 +87,18 @@ _SIGNATURES = {
     'mnrf_encode': (C.c_int, [C.POINTER(EncodeDesc)] + [_P] * 11),
     'mnrf_viewdir_enc': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),
-    'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 10),
+    'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 11),
     'mnrf_head_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P, _P]),
     'mnrf_head_bwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P,
                                 C.c_int64, C.c_int32, _P, _P, _P, _P]),
     'mnrf_colsum': (C.c_int, [C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
-    'mnrf_composite_fwd': (C.c_int, [C.POINTER(CompositeDesc)] + [_P] * 16),
-    'mnrf_composite_bwd': (C.c_int, [C.POINTER(LossDesc)] + [_P] * 21),
+    'mnrf_composite_fwd': (C.c_int, [C.POINTER(CompositeDesc)] + [_P] * 18),
+    'mnrf_composite_bwd': (C.c_int, [C.POINTER(LossDesc)] + [_P] * 24),
+    'mnrf_encode_tangent': (C.c_int, [C.POINTER(EncodeDesc)] + [_P] * 9 + [C.c_int32, _P]),
+    'mnrf_refdir_fwd': (C.c_int, [C.POINTER(RefdirDesc)] + [_P] * 10 + [C.c_float, C.c_float, C.c_int32, _P, _P]),
+    'mnrf_refdir_bwd': (C.c_int, [C.POINTER(RefdirDesc)] + [_P] * 8 + [C.c_int32, C.c_float, C.c_float, C.c_int32] +
+                        [_P] * 8),
+    'mnrf_outer_mask': (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, _P]),
     'mnrf_clip_adam': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 6),
     'mnrf_clip_adam_dyn': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 7),
     'mnrf_pack_weights': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -45,22 +45,25 @@ class DenseSpec:
 
 
 class MLPPlan:
-  """Static layout of one MLP: layer table, buffer widths, flat parameter offsets."""
+  """Static layout of one MLP: layer table (flax creation order), buffer widths, flat offsets."""
+
+  HEAD_SLOTS = {'density': (0, 1), 'grad_pred': (1, 3), 'diffuse': (4, 3), 'tint': (7, 3),
+                'roughness': (10, 1)}     # column slots of the head-gradient slab (csrc/refnerf.cu)
 
   def __init__(self, cfg: configs.MLPConfig, use_viewdirs=True):
     cfg.validate()
-    unsupported = [k for k in ('use_reflections', 'use_directional_enc', 'enable_pred_roughness',
-                               'use_diffuse_color', 'use_specular_tint', 'use_n_dot_v',
-                               'enable_pred_normals') if getattr(cfg, k)]
-    if unsupported or not cfg.disable_density_normals:
-      raise NotImplementedError(
-          'CUDA path: Ref-NeRF branches (%s, density normals) are a later milestone '
-          '(DESIGN.md scope table)' % ', '.join(unsupported))
-    if cfg.net_activation != 'relu' or cfg.density_activation != 'softplus':
-      raise NotImplementedError('CUDA path supports relu trunk / softplus density')
+    if cfg.net_activation != 'relu' or cfg.density_activation != 'softplus' or \
+       cfg.roughness_activation != 'softplus':
+      raise NotImplementedError('CUDA path supports relu trunk / softplus density and roughness')
     if cfg.bottleneck_noise > 0:
       raise NotImplementedError('bottleneck_noise is not wired into the CUDA path yet')
+    if cfg.num_rgb_channels != 3:
+      raise NotImplementedError('num_rgb_channels != 3')
     self.cfg = cfg
+    self.density_normals = not cfg.disable_density_normals
+    self.pred_normals = cfg.enable_pred_normals
+    if self.density_normals and cfg.warp_fn is not None:
+      raise NotImplementedError('density normals through a contraction warp')
     self.basis = np.ascontiguousarray(
         geopoly.generate_basis(cfg.basis_shape, cfg.basis_subdivisions), dtype=np.float32)
     self.K = self.basis.shape[0]
@@ -72,74 +75,96 @@ class MLPPlan:
     self.device_constraints = [('net_width', W)]
     specs: List[DenseSpec] = []
     k = 0
+
+    def add(role, in_dim, in_pad, out_dim, head, act=L.ACT_NONE, rm=None):
+      nonlocal k
+      specs.append(DenseSpec(f'Dense_{k}', role, in_dim, in_pad, out_dim, head, act, rm))
+      k += 1
     x_dim, x_pad, x_has_feat = self.F, self.Fpad, False
-    self.trunk_in = []        # per trunk layer: (width part, has concatenated features)
     self.concat_after = []    # trunk layers whose output is concatenated with the features
     for i in range(cfg.net_depth):
-      rm = None
-      if x_has_feat:
-        rm = np.concatenate([np.arange(W), W + np.arange(self.F)])
-      specs.append(DenseSpec(f'Dense_{k}', 'trunk', x_dim, x_pad, W, False, L.ACT_RELU, rm))
-      k += 1
+      rm = np.concatenate([np.arange(W), W + np.arange(self.F)]) if x_has_feat else None
+      add('trunk', x_dim, x_pad, W, False, L.ACT_RELU, rm)
       if i % cfg.skip_layer == 0 and i > 0:
         self.concat_after.append(i)
         x_dim, x_pad, x_has_feat = W + self.F, W + self.Fpad, True
       else:
         x_dim, x_pad, x_has_feat = W, W, False
     self.last_has_feat = x_has_feat
-    rm = np.concatenate([np.arange(W), W + np.arange(self.F)]) if x_has_feat else None
-    specs.append(DenseSpec(f'Dense_{k}', 'density', x_dim, x_pad, 1, True, row_map=rm))
-    k += 1
+    self.x_dim, self.x_pad = x_dim, x_pad
+    rmx = np.concatenate([np.arange(W), W + np.arange(self.F)]) if x_has_feat else None
+    add('density', x_dim, x_pad, 1, True, rm=rmx)
+    if self.pred_normals:
+      add('grad_pred', x_dim, x_pad, 3, True, rm=rmx)
     self.has_rgb = not cfg.disable_rgb
     self.use_viewdirs = use_viewdirs
+    self.ref_stage = False
+    if (self.pred_normals or self.density_normals) and not self.has_rgb:
+      raise NotImplementedError('normals on an MLP with disable_rgb (no consumer on the CUDA path)')
     if self.has_rgb:
       if not use_viewdirs:
         raise NotImplementedError('use_viewdirs=False with rgb is not wired into the CUDA path')
       if cfg.bottleneck_width <= 0:
         raise NotImplementedError('bottleneck_width == 0 is not supported (models.py:536-554)')
+      if cfg.use_diffuse_color:
+        add('diffuse', x_dim, x_pad, 3, True, rm=rmx)
+      if cfg.use_specular_tint:
+        add('tint', x_dim, x_pad, 3, True, rm=rmx)
+      if cfg.enable_pred_roughness:
+        add('roughness', x_dim, x_pad, 1, True, rm=rmx)
+      if cfg.use_directional_enc and not cfg.enable_pred_roughness:
+        raise NotImplementedError('IDE without a predicted roughness (kappa_inv would be None)')
       bw = cfg.bottleneck_width
       self.device_constraints.append(('bottleneck_width', bw))
-      specs.append(DenseSpec(f'Dense_{k}', 'bottleneck', x_dim, x_pad, bw, False, L.ACT_NONE, rm))
-      k += 1
-      self.dir_dim = 3 + 6 * cfg.deg_view
-      vin, vin_pad = bw + self.dir_dim, _pad64(bw + self.dir_dim)
+      add('bottleneck', x_dim, x_pad, bw, False, L.ACT_NONE, rmx)
+      self.ref_stage = (self.pred_normals or self.density_normals or cfg.use_reflections or
+                        cfg.use_directional_enc or cfg.use_n_dot_v)
+      if cfg.use_directional_enc:
+        from . import ref_utils
+        self.dir_dim = ref_utils.ide_dim(cfg.deg_view)
+      else:
+        self.dir_dim = 3 + 6 * cfg.deg_view
+      vin = bw + self.dir_dim + (1 if cfg.use_n_dot_v else 0)
+      vin_pad = _pad64(vin)
+      if self.ref_stage and vin_pad - bw < 11:
+        vin_pad += 64
       self.vin_dim, self.vin_pad = vin, vin_pad
       Wv = cfg.net_width_viewdirs
       self.device_constraints.append(('net_width_viewdirs', Wv))
-      v_dim, v_pad, v_has_in = vin, vin_pad, True
+      v_dim, v_pad, v_has_in = vin, vin_pad, False
       self.view_concat_after = []
       for i in range(cfg.net_depth_viewdirs):
-        if i == 0:
-          rmv = None
-        elif v_has_in:
-          rmv = np.concatenate([np.arange(Wv), Wv + np.arange(vin)])
-        else:
-          rmv = None
-        specs.append(DenseSpec(f'Dense_{k}', 'view', v_dim, v_pad, Wv, False, L.ACT_RELU, rmv))
-        k += 1
+        rmv = np.concatenate([np.arange(Wv), Wv + np.arange(vin)]) if v_has_in else None
+        add('view', v_dim, v_pad, Wv, False, L.ACT_RELU, rmv)
         if i % cfg.skip_layer_dir == 0 and i > 0:
           self.view_concat_after.append(i)
           v_dim, v_pad, v_has_in = Wv + vin, Wv + vin_pad, True
         else:
           v_dim, v_pad, v_has_in = Wv, Wv, False
-      if self.view_concat_after:
-        raise NotImplementedError('skip connections inside the view MLP (net_depth_viewdirs > 4)')
-      specs.append(DenseSpec(f'Dense_{k}', 'rgb', v_dim, v_pad, cfg.num_rgb_channels, True))
-      k += 1
+      if len(self.view_concat_after) > 1:
+        raise NotImplementedError('more than one skip connection inside the view MLP')
+      rmv = np.concatenate([np.arange(Wv), Wv + np.arange(vin)]) if v_has_in else None
+      if cfg.net_depth_viewdirs == 0:
+        raise NotImplementedError('net_depth_viewdirs == 0')
+      add('rgb', v_dim, v_pad, cfg.num_rgb_channels, True, rm=rmv)
     off = 0
-    for s in specs:
-      s.w_off = off
-      off += s.in_pad * s.out_dim
+    for sp in specs:
+      sp.w_off = off
+      off += sp.in_pad * sp.out_dim
       off = (off + 3) // 4 * 4
-      s.b_off = off
-      off += s.out_dim
+      sp.b_off = off
+      off += sp.out_dim
       off = (off + 3) // 4 * 4
     self.specs = specs
     self.flat_size = off
-    self.num_params = sum(s.in_dim * s.out_dim + s.out_dim for s in specs)
+    self.num_params = sum(sp.in_dim * sp.out_dim + sp.out_dim for sp in specs)
 
   def by_role(self, role):
-    return [s for s in self.specs if s.role == role]
+    return [sp for sp in self.specs if sp.role == role]
+
+  def one(self, role):
+    r = self.by_role(role)
+    return r[0] if r else None
 
 
 class MLPDevice:
@@ -151,10 +176,10 @@ class MLPDevice:
     self.device = device
     self.basis = torch.tensor(plan.basis, device=device)
     self.w_nk, self.w_kn, self.colv = {}, {}, {}
-    for s in plan.specs:
-      self.w_nk[s.name] = torch.zeros(s.out_dim, s.in_pad, device=device, dtype=torch.bfloat16)
-      if not s.head:
-        self.w_kn[s.name] = torch.zeros(s.in_pad, s.out_dim, device=device, dtype=torch.bfloat16)
+    for sp in plan.specs:
+      self.w_nk[sp.name] = torch.zeros(sp.out_dim, sp.in_pad, device=device, dtype=torch.bfloat16)
+      if not sp.head:
+        self.w_kn[sp.name] = torch.zeros(sp.in_pad, sp.out_dim, device=device, dtype=torch.bfloat16)
     self.repack()
 
   def W(self, s, buf=None):
@@ -167,10 +192,30 @@ class MLPDevice:
 
   def repack(self):
     """fp32 master -> bf16 operand layouts (after init and after every optimizer step)."""
-    for s in self.plan.specs:
-      ops.pack_weights(self.W(s), self.w_nk[s.name], self.w_kn.get(s.name))
-    d = self.plan.by_role('density')[0]
+    plan = self.plan
+    for sp in plan.specs:
+      ops.pack_weights(self.W(sp), self.w_nk[sp.name], self.w_kn.get(sp.name))
+    d = plan.one('density')
     self.colv_density = self.w_nk[d.name][0].float().contiguous()   # bf16-rounded, as the fwd used
+    if plan.ref_stage:
+      # [x_pad, vin_pad] K-major B operand of the trunk-entry dgrad:  [ W_bottleneck | head weights ]
+      bt = plan.one('bottleneck')
+      bw = bt.out_dim
+      if not hasattr(self, 'wcat_kn'):
+        self.wcat_kn = torch.zeros(plan.x_pad, plan.vin_pad, device=self.device, dtype=torch.bfloat16)
+      self.wcat_kn[:, :bw] = self.w_kn[bt.name]
+      for role, (c0, n) in plan.HEAD_SLOTS.items():
+        sp = plan.one(role)
+        if sp is not None:
+          self.wcat_kn[:, bw + c0:bw + c0 + n] = self.w_nk[sp.name].t()
+
+  def ide_tables(self):
+    if not hasattr(self, '_ide'):
+      from . import ref_utils
+      m, l, mat = ref_utils.ide_tables(self.plan.cfg.deg_view)
+      self._ide = (torch.tensor(mat, dtype=torch.float32, device=self.device).contiguous(),
+                   torch.tensor(np.stack([m, l]), dtype=torch.int32, device=self.device).contiguous(), len(m))
+    return self._ide
 
 
 class LevelState:
@@ -362,7 +407,8 @@ class Model:
                 density_bias=cfg.density_bias, density_noise=cfg.density_noise,
                 rgb_activation=cfg.rgb_activation, rgb_premultiplier=cfg.rgb_premultiplier,
                 rgb_bias=cfg.rgb_bias, rgb_padding=cfg.rgb_padding,
-                bg_const=self.mcfg.bg_intensity_range[0])
+                bg_const=self.mcfg.bg_intensity_range[0],
+                rgb_mode=1 if (cfg.use_diffuse_color and not cfg.disable_rgb) else 0)
 
   # ------------------------------------------------------------------ buffers
   def _level_state(self, key, mname, B, S):
@@ -374,41 +420,77 @@ class Model:
     st.B, st.S, st.mname = B, S, mname
     M = B * S
     dev = self.device
-    W = plan.cfg.net_width
+    cfg = plan.cfg
+    W = cfg.net_width
     bf = torch.bfloat16
     st.sdist = torch.empty(B, S + 1, device=dev)
-    # trunk activations; the layer whose output is concatenated with the features owns the
-    # feature columns (encode writes there), otherwise features get their own buffer
-    st.acts, st.bits = [], []       # bf16 activations + 1-bit ReLU masks (32 columns per word)
-    for i in range(plan.cfg.net_depth):
-      width = W + plan.Fpad if i in plan.concat_after else W
-      st.acts.append(torch.empty(M, width, device=dev, dtype=bf))
-      st.bits.append(torch.empty(M, W // 32, device=dev, dtype=torch.int32))
-    if plan.concat_after:
-      st.feat = st.acts[plan.concat_after[0]][:, W:]
-      st.feat_copies = [st.acts[i][:, W:] for i in plan.concat_after[1:]]
-    else:
-      st.feat = torch.empty(M, plan.Fpad, device=dev, dtype=bf)
-      st.feat_copies = []
+
+    def trunk_buffers(rows):
+      # the layer whose output is concatenated with the features owns the feature columns
+      # (encode writes there), otherwise features get their own buffer
+      acts = [torch.empty(rows, W + plan.Fpad if i in plan.concat_after else W, device=dev, dtype=bf)
+              for i in range(cfg.net_depth)]
+      if plan.concat_after:
+        feat = acts[plan.concat_after[0]][:, W:]
+        copies = [acts[i][:, W:] for i in plan.concat_after[1:]]
+      else:
+        feat, copies = torch.empty(rows, plan.Fpad, device=dev, dtype=bf), []
+      return acts, feat, copies
+    st.acts, st.feat, st.feat_copies = trunk_buffers(M)
+    st.bits = [torch.empty(M, W // 32, device=dev, dtype=torch.int32) for _ in range(cfg.net_depth)]
     st.raw_density = torch.empty(B, S, device=dev)
     st.d_raw_density = torch.empty(B, S, device=dev)
+    st.raw_rgb = st.d_raw_rgb = None
+    st.heads, st.d_heads = {}, {}
+    st.extra_dw = None
+    st.normals = st.normals_pred = st.roughness = None
+    if plan.density_normals:
+      # forward-mode tangents d(.)/d(mean_x|y|z), three stacked streams of M rows
+      st.tacts, st.tfeat, st.tfeat_copies = trunk_buffers(3 * M)
+      st.rgd = torch.empty(3, M, device=dev)
+      st.d_rgd = torch.empty(3, M, device=dev)
+      st.normals = torch.empty(M, 3, device=dev)
     if plan.has_rgb:
-      st.vin = torch.empty(M, plan.vin_pad, device=dev, dtype=bf)
-      st.vacts = [torch.empty(M, plan.cfg.net_width_viewdirs, device=dev, dtype=bf)
-                  for _ in range(plan.cfg.net_depth_viewdirs)]
-      st.vbits = [torch.empty(M, plan.cfg.net_width_viewdirs // 32, device=dev, dtype=torch.int32)
-                  for _ in range(plan.cfg.net_depth_viewdirs)]
+      Wv = cfg.net_width_viewdirs
+      nv = cfg.net_depth_viewdirs
+      st.vacts = [torch.empty(M, Wv + plan.vin_pad if i in plan.view_concat_after else Wv, device=dev, dtype=bf)
+                  for i in range(nv)]
+      st.vbits = [torch.empty(M, Wv // 32, device=dev, dtype=torch.int32) for _ in range(nv)]
+      if plan.view_concat_after:
+        st.vin = st.vacts[plan.view_concat_after[0]][:, Wv:]
+      else:
+        st.vin = torch.empty(M, plan.vin_pad, device=dev, dtype=bf)
       st.raw_rgb = torch.empty(B, S, 3, device=dev)
       st.d_raw_rgb = torch.empty(B, S, 3, device=dev)
-    else:
-      st.raw_rgb = None
-      st.d_raw_rgb = None
-    st.dy = None   # gradient ping-pong buffers, allocated on first backward
+      for role in ('grad_pred', 'diffuse', 'tint', 'roughness'):
+        sp = plan.one(role)
+        if sp is not None:
+          st.heads[role] = torch.empty(M, sp.out_dim, device=dev)
+          st.d_heads[role] = torch.empty(M, sp.out_dim, device=dev)
+      if plan.ref_stage:
+        if plan.pred_normals:
+          st.normals_pred = torch.empty(M, 3, device=dev)
+        if cfg.enable_pred_roughness:
+          st.roughness = torch.empty(M, device=dev)
+        st.extra_dw = torch.empty(B, S, device=dev)
+    st.bwd = None   # backward scratch, allocated on first backward
     self._levels[key] = st
     return st
 
+  def _refdir_desc(self, st, plan):
+    cfg = plan.cfg
+    bw = cfg.bottleneck_width
+    ide_n = self.mlps[st.mname].ide_tables()[2] if cfg.use_directional_enc else 0
+    return ops.refdir_desc(
+        st.B * st.S, st.S, use_pred_normals=plan.pred_normals, use_density_normals=plan.density_normals,
+        use_reflections=cfg.use_reflections, use_ide=cfg.use_directional_enc, use_n_dot_v=cfg.use_n_dot_v,
+        use_roughness=cfg.enable_pred_roughness, deg_view=cfg.deg_view, ide_n=ide_n,
+        roughness_bias=cfg.roughness_bias, ld=0, col0=bw, col_end=plan.vin_pad)
+
   # ------------------------------------------------------------------ forward
-  def _mlp_forward(self, st: LevelState, mlp: MLPDevice, rays, impl=0):
+  def _mlp_forward(self, st: LevelState, mlp: MLPDevice, rays, impl=0, loss_mults=None):
+    """loss_mults = (orientation, predicted-normal) multipliers of this level divided by the number
+    of rays, + orientation target flag: when given, the Ref-NeRF stage also emits d(loss)/d(weights)."""
     plan = mlp.plan
     cfg = plan.cfg
     B, S = st.B, st.S
@@ -418,31 +500,60 @@ class Model:
     ops.encode(st.sdist, rays.origins, rays.directions, rays.radii_flat, rays.near_flat,
                rays.far_flat, mlp.basis, min_deg=cfg.min_deg_point, max_deg=cfg.max_deg_point,
                raydist_fn=m.raydist_fn, ray_shape=m.ray_shape, warp_contract=cfg.warp_fn == 'contract',
-               disable_integration=m.disable_integration, feat=st.feat, feat_cols=plan.Fpad)
+               disable_integration=m.disable_integration, feat=st.feat, feat_cols=plan.Fpad,
+               tfeat=st.tfeat if plan.density_normals else None)
     for c in st.feat_copies:
       c.copy_(st.feat)
     x = st.feat
     trunk = plan.by_role('trunk')
-    for i, s in enumerate(trunk):
-      out = st.acts[i][:, :W]
-      ops.gemm(L.GEMM_FWD, x, mlp.w_nk[s.name], out, m=M, n=W, k=s.in_pad, act=L.ACT_RELU,
-               bias=mlp.b(s), maskbits=st.bits[i], impl=impl)
+    for i, sp in enumerate(trunk):
+      ops.gemm(L.GEMM_FWD, x, mlp.w_nk[sp.name], st.acts[i][:, :W], m=M, n=W, k=sp.in_pad, act=L.ACT_RELU,
+               bias=mlp.b(sp), maskbits=st.bits[i], impl=impl)
       x = st.acts[i]          # full width (incl. concatenated features) feeds the next layer
     st.x_last = x
-    d = plan.by_role('density')[0]
+    d = plan.one('density')
     ops.head_fwd(x, mlp.w_nk[d.name], mlp.b(d), 1, d.in_pad, raw=st.raw_density.view(M, 1))
-    if plan.has_rgb:
-      bt = plan.by_role('bottleneck')[0]
-      ops.gemm(L.GEMM_FWD, x, mlp.w_nk[bt.name], st.vin[:, :bt.out_dim], m=M, n=bt.out_dim,
-               k=bt.in_pad, act=L.ACT_NONE, bias=mlp.b(bt), impl=impl)
+    if plan.density_normals:
+      # raw_grad_density = d raw_density / d mean by forward mode (replaces vmap(value_and_grad),
+      # models.py:473-492): tangents see the same weights, no bias, and the primal's ReLU masks
+      for c in st.tfeat_copies:
+        c.copy_(st.tfeat)
+      t = st.tfeat
+      for i, sp in enumerate(trunk):
+        ops.gemm(L.GEMM_DGRAD, t, mlp.w_nk[sp.name], st.tacts[i][:, :W], m=3 * M, n=W, k=sp.in_pad,
+                 maskbits=st.bits[i], mask_mod=M, impl=impl)
+        t = st.tacts[i]
+      st.t_last = t
+      ops.head_fwd(t, mlp.w_nk[d.name], None, 1, d.in_pad, raw=st.rgd.view(3 * M, 1))
+    if not plan.has_rgb:
+      return
+    for role in ('grad_pred', 'diffuse', 'tint', 'roughness'):
+      sp = plan.one(role)
+      if sp is not None:
+        ops.head_fwd(x, mlp.w_nk[sp.name], mlp.b(sp), sp.out_dim, sp.in_pad, raw=st.heads[role])
+    bt = plan.one('bottleneck')
+    ops.gemm(L.GEMM_FWD, x, mlp.w_nk[bt.name], st.vin[:, :bt.out_dim], m=M, n=bt.out_dim,
+             k=bt.in_pad, act=L.ACT_NONE, bias=mlp.b(bt), impl=impl)
+    if plan.ref_stage:
+      desc = self._refdir_desc(st, plan)
+      desc.ld = st.vin.stride(0)
+      mat, ml, _ = mlp.ide_tables() if cfg.use_directional_enc else (None, None, 0)
+      om, pm, on_pred = loss_mults if loss_mults is not None else (0.0, 0.0, True)
+      ops.refdir_fwd(desc, mat, ml, st.heads.get('grad_pred'), st.heads.get('roughness'),
+                     st.rgd if plan.density_normals else None, rays.viewdirs, st.normals_pred, st.normals,
+                     st.roughness, st.vin, om, pm, on_pred,
+                     st.extra_dw if loss_mults is not None else None)
+    else:
       ops.viewdir_enc(rays.viewdirs, S, cfg.deg_view, st.vin, bt.out_dim, plan.vin_pad)
-      v = st.vin
-      for i, s in enumerate(plan.by_role('view')):
-        ops.gemm(L.GEMM_FWD, v, mlp.w_nk[s.name], st.vacts[i], m=M, n=s.out_dim, k=s.in_pad,
-                 act=L.ACT_RELU, bias=mlp.b(s), maskbits=st.vbits[i], impl=impl)
-        v = st.vacts[i]
-      r = plan.by_role('rgb')[0]
-      ops.head_fwd(v, mlp.w_nk[r.name], mlp.b(r), r.out_dim, r.in_pad, raw=st.raw_rgb.view(M, 3))
+    v = st.vin
+    for i, sp in enumerate(plan.by_role('view')):
+      Wv = sp.out_dim
+      ops.gemm(L.GEMM_FWD, v, mlp.w_nk[sp.name], st.vacts[i][:, :Wv], m=M, n=Wv, k=sp.in_pad,
+               act=L.ACT_RELU, bias=mlp.b(sp), maskbits=st.vbits[i], impl=impl)
+      v = st.vacts[i]
+    st.v_last = v
+    r = plan.one('rgb')
+    ops.head_fwd(v, mlp.w_nk[r.name], mlp.b(r), r.out_dim, r.in_pad, raw=st.raw_rgb.view(M, 3))
 
   def _prep_rays(self, rays):
     r = utils.to_device_flat(rays, self.device)
@@ -451,7 +562,18 @@ class Model:
     r.far_flat = r.far[:, 0].contiguous()
     return r
 
-  def forward_levels(self, rng, rays, train_frac, compute_extras, want_samples, impl=0, anneal_dev=None):
+  def level_loss_mults(self, config, i_level, B):
+    """(orientation, predicted-normal) multipliers of level i divided by the ray count, target flag
+    (train_utils.py:162-197)."""
+    fine = i_level == self.mcfg.num_levels - 1
+    om = config.orientation_loss_mult if fine else config.orientation_coarse_loss_mult
+    pm = config.predicted_normal_loss_mult if fine else config.predicted_normal_coarse_loss_mult
+    if config.orientation_loss_target not in ('normals', 'normals_pred'):
+      raise ValueError(f'orientation_loss_target {config.orientation_loss_target!r}')
+    return om / B, pm / B, config.orientation_loss_target == 'normals_pred'
+
+  def forward_levels(self, rng, rays, train_frac, compute_extras, want_samples, impl=0, anneal_dev=None,
+                     loss_config=None):
     """Runs all levels; returns the list of LevelState (buffers stay valid until the next call)."""
     if self.params is None:
       raise RuntimeError('Model has no parameters: call construct_model()/init() first')
@@ -493,7 +615,16 @@ class Model:
                        use_dilation=lv['use_dilation'], domain=(s_near, s_far), anneal=lv['anneal'],
                        resample_padding=m.resample_padding, jitter=jit, single_jitter=m.single_jitter,
                        u_base=u_base, max_jitter=max_jitter, out=st.sdist, anneal_dev=anneal_dev)
-      self._mlp_forward(st, mlp, rays, impl=impl)
+      st.loss_mults = self.level_loss_mults(loss_config, i, B) if (loss_config is not None and
+                                                                   mlp.plan.ref_stage) else None
+      if st.loss_mults is not None:
+        om, pm, on_pred = st.loss_mults
+        if (om > 0 and ((on_pred and not mlp.plan.pred_normals) or (not on_pred and not mlp.plan.density_normals))):
+          raise ValueError('Normals cannot be None if orientation loss is on.')
+        if pm > 0 and not (mlp.plan.pred_normals and mlp.plan.density_normals):
+          raise ValueError('Predicted normals and gradient normals cannot be None if '
+                           'predicted normal loss is on.')
+      self._mlp_forward(st, mlp, rays, impl=impl, loss_mults=st.loss_mults)
       st.noise = None
       if mlp.plan.cfg.density_noise > 0 and rng is not None:
         if isinstance(rng, dict):
@@ -504,6 +635,7 @@ class Model:
       st.comp = ops.composite_fwd(st.raw_density, st.raw_rgb, st.sdist, rays.directions,
                                   rays.near_flat, rays.far_flat, cfg=st.comp_cfg,
                                   density_noise=st.noise, rgb_scale=rgb_scale if st.raw_rgb is not None else None,
+                                  raw_diffuse=st.heads.get('diffuse'), raw_tint=st.heads.get('tint'),
                                   want_samples=want_samples, want_extras=compute_extras)
       st.rgb_scale = rgb_scale if st.raw_rgb is not None else None
       sdist_prev, w_prev = st.sdist, st.comp['weights']
@@ -527,6 +659,10 @@ class Model:
         for j, k in enumerate(['distance_mean', 'distance_percentile_5', 'distance_median',
                                'distance_percentile_95']):
           rend[k] = c['dist'][:, j].contiguous().view(lead)
+        w3 = c['weights'][..., None]
+        for k, v in (('normals', st.normals), ('normals_pred', st.normals_pred), ('roughness', st.roughness)):
+          if v is not None:     # volumetric_rendering extras (render.py:186-189)
+            rend[k] = (w3 * v.view(st.B, st.S, -1)).sum(-2).view(lead + (-1,))
         rend['ray_sdist'] = st.sdist[:n_vis].clone()
         rend['ray_weights'] = c['weights'][:n_vis].clone()
         rend['ray_rgbs'] = c['rgb_samples'][:n_vis].clone()
@@ -534,7 +670,11 @@ class Model:
       S = st.S
       ray_history.append(dict(
           density=c['density'].view(lead + (S,)), rgb=c['rgb_samples'].view(lead + (S, 3)),
-          raw_grad_density=None, grad_pred=None, normals=None, normals_pred=None, roughness=None,
+          raw_grad_density=None if st.normals is None else st.rgd.t().reshape(lead + (S, 3)),
+          grad_pred=None if 'grad_pred' not in st.heads else st.heads['grad_pred'].view(lead + (S, 3)),
+          normals=None if st.normals is None else st.normals.view(lead + (S, 3)),
+          normals_pred=None if st.normals_pred is None else st.normals_pred.view(lead + (S, 3)),
+          roughness=None if st.roughness is None else st.roughness.view(lead + (S, 1)),
           sdist=st.sdist.clone().view(lead + (S + 1,)), weights=c['weights'].view(lead + (S,))))
     if compute_extras:
       final_rgb = (renderings[-1]['ray_rgbs'] * renderings[-1]['ray_weights'][..., None]).sum(-2)
@@ -549,7 +689,7 @@ class Model:
     return self(rng, rays, train_frac, compute_extras, zero_glo)
 
   # ------------------------------------------------------------------ backward
-  def _mlp_backward(self, st: LevelState, mlp: MLPDevice, impl=0):
+  def _mlp_backward(self, st: LevelState, mlp: MLPDevice, rays=None, impl=0, loss_mults=None, stats=None):
     """Accumulates parameter gradients of one level into mlp.grads (fp32).
 
     Bias gradients are column sums of the dY buffers; each is reduced inside the kernel that
@@ -560,58 +700,113 @@ class Model:
     M = st.B * st.S
     W = cfg.net_width
     dev = self.device
-    if st.dy is None:
-      st.dy = [torch.empty(M, W, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    bf = torch.bfloat16
+    if st.bwd is None:
+      bw_ = LevelState()
+      bw_.dy = [torch.empty(M, W, device=dev, dtype=bf) for _ in range(2)]
+      if plan.has_rgb:
+        Wv = cfg.net_width_viewdirs
+        bw_.dv = [torch.empty(M, Wv, device=dev, dtype=bf) for _ in range(2)]
+        bw_.d_vin = torch.empty(M, plan.vin_pad, device=dev, dtype=bf)
+        bw_.d_vin_skip = torch.empty(M, plan.vin_pad, device=dev, dtype=bf) if plan.view_concat_after else None
+      if plan.density_normals:
+        bw_.h = [torch.empty(3 * M, W, device=dev, dtype=bf) for _ in range(2)]
+      st.bwd = bw_
+    sc = st.bwd
     g = mlp.grads
-    d = plan.by_role('density')[0]
+    d = plan.one('density')
     trunk = plan.by_role('trunk')
     x_last = st.x_last
-    dy = st.dy[0]
+    dy = sc.dy[0]
     d_raw_density = st.d_raw_density.view(M, 1)
     if plan.has_rgb:
-      r = plan.by_role('rgb')[0]
+      r = plan.one('rgb')
       views = plan.by_role('view')
       Wv = cfg.net_width_viewdirs
-      if not hasattr(st, 'dv'):
-        st.dv = [torch.empty(M, Wv, device=dev, dtype=torch.bfloat16) for _ in range(min(2, len(views)))]
-      dcur = st.dv[0]
-      ops.head_bwd(st.vacts[-1], mlp.w_nk[r.name], st.d_raw_rgb.view(M, 3), r.out_dim, r.in_pad, dx=dcur,
+      bt = plan.one('bottleneck')
+      bw = bt.out_dim
+      dcur = sc.dv[0]
+      ops.head_bwd(st.v_last, mlp.w_nk[r.name], st.d_raw_rgb.view(M, 3), r.out_dim, r.in_pad, dx=dcur,
                    relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g), dxsum=mlp.b(views[-1], g))
+      have_skip_grad = False
       for i in range(len(views) - 1, -1, -1):
-        s = views[i]
+        sp = views[i]
         xin = st.vin if i == 0 else st.vacts[i - 1]
-        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(s, g), m=s.in_pad, n=s.out_dim, k=M, impl=impl)
+        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(sp, g), m=sp.in_pad, n=Wv, k=M, impl=impl)
         if i > 0:
-          nxt = st.dv[1] if dcur is st.dv[0] else st.dv[0]
-          ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s.name], nxt, m=M, n=Wv, k=s.out_dim,
+          if (i - 1) in plan.view_concat_after:
+            # this layer also consumed vin (skip concat): its second gradient contribution
+            ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[sp.name][Wv:], sc.d_vin_skip, m=M, n=plan.vin_pad, k=Wv,
+                     impl=impl)
+            have_skip_grad = True
+          nxt = sc.dv[1] if dcur is sc.dv[0] else sc.dv[0]
+          ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[sp.name], nxt, m=M, n=Wv, k=Wv,
                    maskbits=st.vbits[i - 1], colsum=mlp.b(views[i - 1], g), impl=impl)
           dcur = nxt
       s0 = views[0]
-      bt = plan.by_role('bottleneck')[0]
-      if not hasattr(st, 'dbott'):
-        st.dbott = torch.empty(M, bt.out_dim, device=dev, dtype=torch.bfloat16)
-      # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
-      ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], st.dbott, m=M, n=bt.out_dim, k=s0.out_dim,
-               colsum=mlp.b(bt, g), impl=impl)
-      ops.gemm(L.GEMM_WGRAD, x_last, st.dbott, mlp.W(bt, g), m=bt.in_pad, n=bt.out_dim, k=M, impl=impl)
-      # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
-      ops.gemm(L.GEMM_DGRAD, st.dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bt.out_dim,
-               rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1],
-               colsum=mlp.b(trunk[-1], g), impl=impl)
+      if plan.ref_stage:
+        # full d vin: [ d bottleneck | d direction encoding (| d n.v) ]
+        ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], sc.d_vin, m=M, n=plan.vin_pad, k=Wv,
+                 addend=sc.d_vin_skip if have_skip_grad else None, impl=impl)
+        # bias gradient of the bottleneck = column sums of d vin[:, :bw]
+        ops.colsum(sc.d_vin[:, :bw], bw, mlp.b(bt, g))
+        desc = self._refdir_desc(st, plan)
+        desc.ld = st.vin.stride(0)
+        mat, ml, _ = mlp.ide_tables() if cfg.use_directional_enc else (None, None, 0)
+        om, pm, on_pred = loss_mults if loss_mults is not None else (0.0, 0.0, True)
+        ops.refdir_bwd(desc, mat, ml, st.heads.get('grad_pred'), st.heads.get('roughness'),
+                       st.rgd if plan.density_normals else None, rays.viewdirs, st.comp['weights'], sc.d_vin,
+                       om, pm, on_pred, st.d_raw_density, st.d_heads.get('diffuse'), st.d_heads.get('tint'),
+                       st.d_heads.get('grad_pred'), st.d_heads.get('roughness').view(M) if 'roughness' in st.d_heads else None,
+                       st.d_rgd if plan.density_normals else None, stats)
+        # parameter gradients of the narrow heads (x^T d_raw)
+        for role in ('grad_pred', 'diffuse', 'tint', 'roughness'):
+          sp = plan.one(role)
+          if sp is not None:
+            ops.head_bwd(x_last, mlp.w_nk[sp.name], st.d_heads[role], sp.out_dim, sp.in_pad, dx=None,
+                         dw=mlp.W(sp, g), db=mlp.b(sp, g))
+        ops.gemm(L.GEMM_WGRAD, x_last, sc.d_vin[:, :bw], mlp.W(bt, g), m=bt.in_pad, n=bw, k=M, impl=impl)
+        # d x_last = relu'(x_last) * ([d bottleneck | head gradients] @ [W_b | w_heads]^T)
+        ops.gemm(L.GEMM_DGRAD, sc.d_vin, mlp.wcat_kn, dy, m=M, n=W, k=plan.vin_pad,
+                 maskbits=st.bits[-1], colsum=mlp.b(trunk[-1], g), impl=impl)
+      else:
+        dbott = sc.d_vin[:, :bw]
+        # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
+        ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], dbott, m=M, n=bw, k=Wv,
+                 colsum=mlp.b(bt, g), addend=sc.d_vin_skip[:, :bw] if have_skip_grad else None, impl=impl)
+        ops.gemm(L.GEMM_WGRAD, x_last, dbott, mlp.W(bt, g), m=bt.in_pad, n=bw, k=M, impl=impl)
+        # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
+        ops.gemm(L.GEMM_DGRAD, dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bw,
+                 rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1],
+                 colsum=mlp.b(trunk[-1], g), impl=impl)
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=None, dw=mlp.W(d, g),
                    db=mlp.b(d, g))
     else:
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=dy, relu_mask=True,
                    dw=mlp.W(d, g), db=mlp.b(d, g), dxsum=mlp.b(trunk[-1], g))
-    cur, other = st.dy[0], st.dy[1]
+    if plan.density_normals:
+      # adjoint of the tangent chain: H_last = relu'(x_last) * (d_rgd (x) w_density), three streams
+      hcur, hoth = sc.h[0], sc.h[1]
+      ops.outer_mask(st.d_rgd.view(3 * M), mlp.colv_density, st.bits[-1], hcur, rows=3 * M, n=W, mask_mod=M)
+      ops.head_bwd(st.t_last, mlp.w_nk[d.name], st.d_rgd.view(3 * M, 1), 1, d.in_pad, dx=None,
+                   dw=mlp.W(d, g), db=None)
+      for i in range(len(trunk) - 1, -1, -1):
+        sp = trunk[i]
+        tin = st.tfeat if i == 0 else st.tacts[i - 1]
+        ops.gemm(L.GEMM_WGRAD, tin, hcur, mlp.W(sp, g), m=sp.in_pad, n=W, k=3 * M, impl=impl)
+        if i > 0:
+          ops.gemm(L.GEMM_DGRAD, hcur, mlp.w_kn[sp.name], hoth, m=3 * M, n=W, k=W,
+                   maskbits=st.bits[i - 1], mask_mod=M, impl=impl)
+          hcur, hoth = hoth, hcur
+    cur, other = sc.dy[0], sc.dy[1]
     for i in range(len(trunk) - 1, -1, -1):
-      s = trunk[i]
+      sp = trunk[i]
       xin = st.feat if i == 0 else st.acts[i - 1]
-      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(s, g), m=s.in_pad, n=W, k=M, impl=impl)
+      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(sp, g), m=sp.in_pad, n=W, k=M, impl=impl)
       if i > 0:
         # only the hidden part of the input carries gradient (features are constants:
         # stop_gradient(sdist), models.py:200-201)
-        ops.gemm(L.GEMM_DGRAD, cur, mlp.w_kn[s.name], other, m=M, n=W, k=W,
+        ops.gemm(L.GEMM_DGRAD, cur, mlp.w_kn[sp.name], other, m=M, n=W, k=W,
                  maskbits=st.bits[i - 1], colsum=mlp.b(trunk[i - 1], g), impl=impl)
         cur, other = other, cur
 

@@ -82,7 +82,7 @@ def sample_level(sdist_prev, w_prev, num_samples, *, dilation=0.0, use_dilation=
 
 def encode(sdist, origins, directions, radii, near, far, basis, *, min_deg, max_deg,
            raydist_fn=None, ray_shape='cone', warp_contract=False, disable_integration=False,
-           feat=None, feat_cols=None, want_f32=False, want_tdist=False):
+           feat=None, feat_cols=None, want_f32=False, want_tdist=False, tfeat=None):
   """cast_rays + (contract) + lift + IPE -> bf16 features [B*S, ld] (row stride from `feat`)."""
   lib = L.load()
   if ray_shape not in L.RAY_SHAPE:
@@ -102,6 +102,13 @@ def encode(sdist, origins, directions, radii, near, far, basis, *, min_deg, max_
   f32 = torch.empty(B * S, F, device=sdist.device) if want_f32 else None
   tdist = torch.empty(B, S + 1, device=sdist.device) if want_tdist else None
   _count()
+  if tfeat is not None:
+    assert tfeat.dtype == torch.bfloat16 and tfeat.stride(1) == 1 and not want_f32 and not want_tdist
+    L.check(lib.mnrf_encode_tangent(C.byref(d), L.ptr(_f32(sdist)), L.ptr(_f32(origins)),
+                                    L.ptr(_f32(directions)), L.ptr(_f32(radii)), L.ptr(_f32(near)),
+                                    L.ptr(_f32(far)), L.ptr(_f32(basis)), L.ptr(feat), L.ptr(tfeat),
+                                    tfeat.stride(0), L.stream_ptr()))
+    return feat, None, None
   L.check(lib.mnrf_encode(C.byref(d), L.ptr(_f32(sdist)), L.ptr(_f32(origins)),
                           L.ptr(_f32(directions)), L.ptr(_f32(radii)), L.ptr(_f32(near)),
                           L.ptr(_f32(far)), L.ptr(_f32(basis)), L.ptr(feat), L.ptr(f32),
@@ -118,7 +125,7 @@ def viewdir_enc(viewdirs, num_samples, deg, out, col0, col_end):
 
 
 def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv=None, mask=None,
-         maskbits=None, colsum=None, impl=0):
+         maskbits=None, colsum=None, mask_mod=0, addend=None, impl=0):
   """Dense-layer GEMM (see include/mnrf.h).  a/b/out/mask are 2-D views with unit inner stride."""
   lib = L.load()
   for t in (a, b, out) + ((mask,) if mask is not None else ()):
@@ -127,14 +134,15 @@ def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv
     assert maskbits.dtype == torch.int32 and maskbits.stride(-1) == 1
   d = L.GemmDesc(mode, act, m, n, k, a.stride(0), b.stride(0), out.stride(0),
                  mask.stride(0) if mask is not None else 0,
-                 maskbits.stride(0) if maskbits is not None else 0, impl)
+                 maskbits.stride(0) if maskbits is not None else 0,
+                 addend.stride(0) if addend is not None else 0, mask_mod, impl)
   _count()
   ev = None
   if GEMM_EVENTS is not None:
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev[0].record()
   L.check(lib.mnrf_gemm(C.byref(d), L.ptr(a), L.ptr(b), L.ptr(bias), L.ptr(rowv), L.ptr(colv),
-                        L.ptr(mask), L.ptr(maskbits), L.ptr(colsum), L.ptr(out), L.stream_ptr()))
+                        L.ptr(mask), L.ptr(maskbits), L.ptr(colsum), L.ptr(addend), L.ptr(out), L.stream_ptr()))
   if ev is not None:
     ev[1].record()
     GEMM_EVENTS.append((ev[0], ev[1], 2.0 * m * n * k))
@@ -168,16 +176,17 @@ def colsum(x, n, out):
 
 
 def _cdesc(B, S, *, raydist_fn, opaque_background, density_bias, density_noise, rgb_activation,
-           rgb_premultiplier, rgb_bias, rgb_padding, bg_const):
+           rgb_premultiplier, rgb_bias, rgb_padding, bg_const, rgb_mode=0):
   if rgb_activation not in L.RGB_ACT:
     raise ValueError(f'rgb_activation {rgb_activation!r} not supported by the CUDA path')
   return L.CompositeDesc(B, S, L.RAYDIST[raydist_fn], int(opaque_background), float(density_bias),
                          float(density_noise), L.RGB_ACT[rgb_activation], float(rgb_premultiplier),
-                         float(rgb_bias), float(rgb_padding), float(bg_const))
+                         float(rgb_bias), float(rgb_padding), float(bg_const), int(rgb_mode))
 
 
 def composite_fwd(raw_density, raw_rgb, sdist, directions, near, far, *, cfg, density_noise=None,
-                  bg_rgb=None, rgb_scale=None, want_samples=False, want_extras=False):
+                  bg_rgb=None, rgb_scale=None, raw_diffuse=None, raw_tint=None, want_samples=False,
+                  want_extras=False):
   """compute_alpha_weights + volumetric_rendering.  cfg: kwargs of _cdesc."""
   lib = L.load()
   B, S = raw_density.shape
@@ -193,7 +202,8 @@ def composite_fwd(raw_density, raw_rgb, sdist, directions, near, far, *, cfg, de
   L.check(lib.mnrf_composite_fwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
                                  L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
                                  L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
-                                 L.ptr(_f32(bg_rgb)), L.ptr(_f32(rgb_scale)), L.ptr(weights), L.ptr(rgb),
+                                 L.ptr(_f32(bg_rgb)), L.ptr(_f32(rgb_scale)), L.ptr(_f32(raw_diffuse)),
+                                 L.ptr(_f32(raw_tint)), L.ptr(weights), L.ptr(rgb),
                                  L.ptr(dens), L.ptr(rgbs), L.ptr(acc), L.ptr(dist), L.stream_ptr()))
   return dict(weights=weights, rgb=rgb, density=dens, rgb_samples=rgbs, acc=acc, dist=dist)
 
@@ -201,7 +211,8 @@ def composite_fwd(raw_density, raw_rgb, sdist, directions, near, far, *, cfg, de
 def composite_bwd(raw_density, raw_rgb, sdist, directions, near, far, target_rgb, lossmult,
                   inv_denom, stats, *, cfg, loss_type, charb_padding, data_mult, distortion_mult,
                   interlevel_mult, sdist_fine=None, weights_fine=None, density_noise=None,
-                  bg_rgb=None, rgb_scale=None, d_raw_density=None, d_raw_rgb=None, d_rgb_scale=None):
+                  bg_rgb=None, rgb_scale=None, d_raw_density=None, d_raw_rgb=None, d_rgb_scale=None,
+                  raw_diffuse=None, raw_tint=None, extra_dw=None, d_raw_diffuse=None, d_raw_tint=None):
   lib = L.load()
   B, S = raw_density.shape
   dev = raw_density.device
@@ -217,12 +228,12 @@ def composite_bwd(raw_density, raw_rgb, sdist, directions, near, far, target_rgb
   L.check(lib.mnrf_composite_bwd(C.byref(d), L.ptr(_f32(raw_density)), L.ptr(_f32(raw_rgb)),
                                  L.ptr(_f32(density_noise)), L.ptr(_f32(sdist)),
                                  L.ptr(_f32(directions)), L.ptr(_f32(near)), L.ptr(_f32(far)),
-                                 L.ptr(_f32(bg_rgb)), L.ptr(_f32(rgb_scale)), None, None,
-                                 L.ptr(_f32(target_rgb)),
+                                 L.ptr(_f32(bg_rgb)), L.ptr(_f32(rgb_scale)), L.ptr(_f32(raw_diffuse)),
+                                 L.ptr(_f32(raw_tint)), L.ptr(_f32(extra_dw)), L.ptr(_f32(target_rgb)),
                                  L.ptr(_f32(lossmult)), L.ptr(_f32(inv_denom)),
                                  L.ptr(_f32(sdist_fine)), L.ptr(_f32(weights_fine)),
-                                 L.ptr(d_raw_density), L.ptr(d_raw_rgb), L.ptr(d_rgb_scale), L.ptr(stats),
-                                 L.stream_ptr()))
+                                 L.ptr(d_raw_density), L.ptr(d_raw_rgb), L.ptr(d_rgb_scale),
+                                 L.ptr(d_raw_diffuse), L.ptr(d_raw_tint), L.ptr(stats), L.stream_ptr()))
   return d_raw_density, d_raw_rgb
 
 
@@ -246,3 +257,43 @@ def pack_weights(master, w_nk, w_kn):
   _count()
   L.check(lib.mnrf_pack_weights(in_pad, out, L.ptr(master), L.ptr(w_nk), L.ptr(w_kn),
                                 L.stream_ptr()))
+
+
+def refdir_desc(M, S, *, use_pred_normals, use_density_normals, use_reflections, use_ide, use_n_dot_v,
+                use_roughness, deg_view, ide_n, roughness_bias, ld, col0, col_end):
+  return L.RefdirDesc(M, S, int(use_pred_normals), int(use_density_normals), int(use_reflections),
+                      int(use_ide), int(use_n_dot_v), int(use_roughness), deg_view, ide_n,
+                      float(roughness_bias), ld, col0, col_end)
+
+
+def refdir_fwd(desc, ide_mat, ide_ml, grad_pred, raw_rough, raw_grad_density, viewdirs, normals_pred,
+               normals, roughness, slab, orient_mult=0.0, prednorm_mult=0.0, orient_on_pred=True,
+               extra_dw=None):
+  lib = L.load()
+  _count()
+  L.check(lib.mnrf_refdir_fwd(C.byref(desc), L.ptr(ide_mat), L.ptr(ide_ml), L.ptr(_f32(grad_pred)),
+                              L.ptr(_f32(raw_rough)), L.ptr(_f32(raw_grad_density)), L.ptr(_f32(viewdirs)),
+                              L.ptr(normals_pred), L.ptr(normals), L.ptr(roughness), L.ptr(slab),
+                              float(orient_mult), float(prednorm_mult), int(orient_on_pred),
+                              L.ptr(extra_dw), L.stream_ptr()))
+
+
+def refdir_bwd(desc, ide_mat, ide_ml, grad_pred, raw_rough, raw_grad_density, viewdirs, weights, d_slab,
+               orient_mult, prednorm_mult, orient_on_pred, d_raw_density, d_raw_diffuse, d_raw_tint,
+               d_grad_pred, d_raw_rough, d_raw_grad_density, stats):
+  lib = L.load()
+  _count()
+  L.check(lib.mnrf_refdir_bwd(C.byref(desc), L.ptr(ide_mat), L.ptr(ide_ml), L.ptr(_f32(grad_pred)),
+                              L.ptr(_f32(raw_rough)), L.ptr(_f32(raw_grad_density)), L.ptr(_f32(viewdirs)),
+                              L.ptr(_f32(weights)), L.ptr(d_slab), d_slab.stride(0), float(orient_mult),
+                              float(prednorm_mult), int(orient_on_pred), L.ptr(_f32(d_raw_density)),
+                              L.ptr(_f32(d_raw_diffuse)), L.ptr(_f32(d_raw_tint)), L.ptr(d_grad_pred),
+                              L.ptr(d_raw_rough), L.ptr(d_raw_grad_density), L.ptr(stats), L.stream_ptr()))
+
+
+def outer_mask(rowv, colv, maskbits, out, *, rows, n, mask_mod=0):
+  lib = L.load()
+  _count()
+  L.check(lib.mnrf_outer_mask(rows, n, mask_mod, L.ptr(_f32(rowv)), L.ptr(_f32(colv)), L.ptr(maskbits),
+                              maskbits.stride(0) if maskbits is not None else 0, L.ptr(out), out.stride(0),
+                              L.stream_ptr()))

@@ -73,9 +73,6 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
   mcfg = model.mcfg
   if config.data_loss_type not in ('mse', 'charb', 'rawnerf'):
     raise NotImplementedError(f'data_loss_type {config.data_loss_type!r}')
-  if config.orientation_loss_mult > 0 or config.orientation_coarse_loss_mult > 0 or \
-     config.predicted_normal_loss_mult > 0 or config.predicted_normal_coarse_loss_mult > 0:
-    raise NotImplementedError('orientation / predicted-normal losses (Ref-NeRF) are a later milestone')
   if config.weight_decay_mults:
     raise NotImplementedError('weight_decay_mults')
   if use_graph and mcfg.near_anneal_rate is not None:
@@ -100,7 +97,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     stats_buf.zero_()
     states = model.forward_levels(rng if config.randomized else None, rays, train_frac,
                                   compute_extras=False, want_samples=False, impl=impl,
-                                  anneal_dev=anneal_ptr)
+                                  anneal_dev=anneal_ptr, loss_config=config)
     fine = states[-1]
     n = len(states)
     for i in range(n - 1, -1, -1):
@@ -116,13 +113,17 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
           sdist_fine=None if is_fine else fine.sdist,
           weights_fine=None if is_fine else fine.comp['weights'],
           density_noise=st.noise, rgb_scale=st.rgb_scale, d_raw_density=st.d_raw_density,
-          d_raw_rgb=st.d_raw_rgb, d_rgb_scale=_d_scale_buf(st))
+          d_raw_rgb=st.d_raw_rgb, d_rgb_scale=_d_scale_buf(st),
+          raw_diffuse=st.heads.get('diffuse'), raw_tint=st.heads.get('tint'),
+          extra_dw=st.extra_dw if st.loss_mults is not None else None,
+          d_raw_diffuse=st.d_heads.get('diffuse'), d_raw_tint=st.d_heads.get('tint'))
       if st.rgb_scale is not None and mcfg.learned_exposure_scaling:
         # d offsets[idx] += [idx > 0] * exposure_values * d_scale   (adjoint of models.py:262-267)
         eidx = rays.exposure_idx[:, 0].long()
         g = (eidx > 0).to(torch.float32)[:, None] * rays.exposure_values * st.d_rgb_scale
         params.seg('exposure_scaling_offsets', params.grads).view(-1, 3).index_add_(0, eidx, g)
-      model._mlp_backward(st, model.mlps[st.mname], impl=impl)
+      model._mlp_backward(st, model.mlps[st.mname], rays=rays, impl=impl, loss_mults=st.loss_mults,
+                          stats=stats_buf[i])
 
   def _d_scale_buf(st):
     if st.rgb_scale is None:
@@ -252,7 +253,8 @@ class LazyStats(dict):
     b = self._buf.detach().cpu()
     mses = b[:, 1].clone()
     losses = {'data': float(b[:, 0].sum()), 'interlevel': float(b[:, 3].sum()),
-              'distortion': float(b[:, 2].sum())}
+              'distortion': float(b[:, 2].sum()), 'orientation': float(b[:, 4].sum()),
+              'predicted_normals': float(b[:, 5].sum())}
     self.update(mses=mses, psnrs=-10.0 / math.log(10.0) * torch.log(mses), losses=losses,
                 loss=sum(losses.values()))
     self['psnr'] = float(self['psnrs'][-1])

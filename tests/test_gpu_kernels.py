@@ -419,3 +419,187 @@ def test_pack_weights_and_adam(ops):
   ops.clip_adam(pc2, g.cuda(), m.cuda(), v.cuda(), scratch, step=7, lr=1.5e-3, beta1=0.9, beta2=0.999,
                 eps=1e-6, grad_max_val=0.0, grad_max_norm=1e-3)
   assert torch.isfinite(pc2).all()
+
+
+def test_composite_diffuse_specular_mode(ops):
+  """rgb_mode 1 (Ref-NeRF, models.py:588-602): value and gradients vs oracle autograd."""
+  from oracle import o_train
+  rng = np.random.default_rng(31)
+  B, S = 50, 32
+  cfg = dict(CFG, raydist_fn=None, opaque_background=False, density_bias=0.5, rgb_mode=1)
+  _, d, _ = _rays(rng, B)
+  sdist = torch.tensor(np.sort(rng.uniform(0, 1, (B, S + 1)).astype(np.float32), -1))
+  nearv, farv = torch.full((B, 1), 2.0), torch.full((B, 1), 6.0)
+  leaves = [torch.tensor(rng.normal(size=sh).astype(np.float32) * sc, requires_grad=True)
+            for sh, sc in [((B, S), 2.0), ((B, S, 3), 1.0), ((B, S, 3), 1.5), ((B, S, 3), 1.0)]]
+  raw_d, raw_rgb, raw_dif, raw_tint = leaves
+  extra = torch.tensor(rng.normal(size=(B, S)).astype(np.float32) * 1e-3)
+  target = torch.tensor(rng.uniform(0, 1, (B, 3)).astype(np.float32))
+
+  def colour(raw_rgb, raw_dif, raw_tint):
+    spec = torch.sigmoid(raw_tint) * torch.sigmoid(raw_rgb)
+    lin = spec + torch.sigmoid(raw_dif - math.log(3.0))
+    return torch.clamp(o_math.linear_to_srgb(lin), 0.0, 1.0) * (1 + 2 * 0.001) - 0.001
+  _, s_to_t = o_coord.construct_ray_warps(None, nearv, farv)
+  tdist = s_to_t(sdist)
+  dens = torch.nn.functional.softplus(raw_d + 0.5)
+  w = o_render.compute_alpha_weights(dens, tdist, d)[0]
+  c = colour(raw_rgb, raw_dif, raw_tint)
+  pix = o_render.volumetric_rendering(c, w, tdist, 1.0, farv, False)['rgb']
+  loss = ((pix - target) ** 2).sum() / (3 * B) + (w * extra).sum()
+  grads = torch.autograd.grad(loss, leaves)
+  out = ops.composite_fwd(raw_d.detach().cuda(), raw_rgb.detach().cuda(), sdist.cuda(), d.cuda(),
+                          nearv[:, 0].contiguous().cuda(), farv[:, 0].contiguous().cuda(), cfg=cfg,
+                          raw_diffuse=raw_dif.detach().cuda(), raw_tint=raw_tint.detach().cuda(), want_samples=True)
+  close(out['rgb_samples'], c.detach(), msg='diffuse+specular colour')
+  close(out['rgb'], pix.detach(), msg='pixel')
+  stats = torch.zeros(8, device='cuda')
+  d_dif = torch.empty(B, S, 3, device='cuda')
+  d_tint = torch.empty(B, S, 3, device='cuda')
+  g_d, g_rgb = ops.composite_bwd(
+      raw_d.detach().cuda(), raw_rgb.detach().cuda(), sdist.cuda(), d.cuda(), nearv[:, 0].contiguous().cuda(),
+      farv[:, 0].contiguous().cuda(), target.cuda(), torch.ones(B, 1).cuda(), torch.tensor([1.0 / (3 * B)]).cuda(),
+      stats, cfg=cfg, loss_type='mse', charb_padding=0.001, data_mult=1.0, distortion_mult=0.0, interlevel_mult=0.0,
+      raw_diffuse=raw_dif.detach().cuda(), raw_tint=raw_tint.detach().cuda(), extra_dw=extra.cuda(),
+      d_raw_diffuse=d_dif, d_raw_tint=d_tint)
+  for got, ref, name in [(g_d, grads[0], 'd raw_density'), (g_rgb, grads[1], 'd raw_rgb'),
+                         (d_dif, grads[2], 'd raw_diffuse'), (d_tint, grads[3], 'd raw_tint')]:
+    close(got, ref, atol=2e-5 * float(ref.abs().max()), rtol=3e-4, msg=name)
+
+
+@pytest.mark.parametrize('mode', ['refnerf', 'viewdir_pe_normals'])
+def test_refdir_stage_vs_oracle_autograd(ops, mode):
+  """normals / roughness / reflection / IDE (or PE) / n.v slab, the two normal losses, and the
+  adjoint of all of it (csrc/refnerf.cu) against the oracle differentiated by torch autograd."""
+  from multinerf_b200 import ref_utils
+  rng = np.random.default_rng(41)
+  B, S = 37, 8
+  M = B * S
+  ide = mode == 'refnerf'
+  deg = 5 if ide else 4
+  v = rng.normal(size=(B, 3)).astype(np.float32)
+  v /= np.linalg.norm(v, axis=-1, keepdims=True)
+  vt = torch.tensor(v)
+  leaves = [torch.tensor(rng.normal(size=sh).astype(np.float32) * sc, requires_grad=True)
+            for sh, sc in [((B, S, 3), 1.0), ((B, S, 1), 1.0), ((3, B, S), 30.0)]]
+  grad_pred, raw_rough, rgd = leaves
+  w = torch.tensor(rng.uniform(0, 0.2, (B, S)).astype(np.float32))
+  dim = ref_utils.ide_dim(5) if ide else 3 + 6 * deg
+  ncols = dim + 1
+  col0, ld = 64, 64 + 128
+  g_slab = torch.tensor(rng.normal(size=(B, S, ncols)).astype(np.float32)).to(torch.bfloat16).float()
+  om, pm = 0.1 / B, 3e-4 / B
+  # oracle
+  n_pred = -o_coord.l2_normalize(grad_pred)
+  n_den = -o_coord.l2_normalize(rgd.permute(1, 2, 0))
+  rough = torch.nn.functional.softplus(raw_rough - 1.0)
+  if ide:
+    refd = o_coord.reflect(-vt[:, None, :], n_pred)
+    enc = o_coord.generate_ide_fn(5)(refd, rough)
+  else:
+    enc = o_coord.pos_enc(vt, 0, deg)[:, None, :].expand(B, S, dim)
+  ndv = (n_pred * vt[:, None, :]).sum(-1, keepdim=True)
+  slab_o = torch.cat([enc, ndv], -1)
+  l_or = om * (w * torch.clamp((n_pred * -vt[:, None, :]).sum(-1), max=0.0) ** 2).sum()
+  l_pn = pm * (w * (1.0 - (n_den * n_pred).sum(-1))).sum()
+  loss = (slab_o * g_slab).sum() + l_or + l_pn
+  grads = torch.autograd.grad(loss, leaves)
+  # device
+  m, l, mat = ref_utils.ide_tables(5)
+  mat_d = torch.tensor(mat, dtype=torch.float32).cuda().contiguous()
+  ml_d = torch.tensor(np.stack([m, l]), dtype=torch.int32).cuda().contiguous()
+  desc = ops.refdir_desc(M, S, use_pred_normals=True, use_density_normals=True, use_reflections=ide, use_ide=ide,
+                         use_n_dot_v=True, use_roughness=True, deg_view=deg, ide_n=len(m), roughness_bias=-1.0,
+                         ld=ld, col0=col0, col_end=ld)
+  slab = torch.full((M, ld), 5.0, dtype=torch.bfloat16, device='cuda')
+  npd, nd_, rgh, edw = (torch.empty(M, 3, device='cuda'), torch.empty(M, 3, device='cuda'),
+                        torch.empty(M, device='cuda'), torch.empty(M, device='cuda'))
+  gp_c = grad_pred.detach().reshape(M, 3).contiguous().cuda()
+  rr_c = raw_rough.detach().reshape(M).contiguous().cuda()
+  rgd_c = rgd.detach().reshape(3, M).contiguous().cuda()
+  ops.refdir_fwd(desc, mat_d, ml_d, gp_c, rr_c, rgd_c, vt.cuda(), npd, nd_, rgh, slab, om, pm, True, edw)
+  torch.cuda.synchronize()
+  close(npd.cpu().view(B, S, 3), n_pred.detach(), msg='normals_pred')
+  close(nd_.cpu().view(B, S, 3), n_den.detach(), atol=1e-5, rtol=1e-4, msg='normals')
+  close(rgh.cpu().view(B, S, 1), rough.detach(), msg='roughness')
+  got = slab.float().cpu().view(B, S, ld)
+  close(got[..., col0:col0 + ncols], slab_o.detach().to(torch.bfloat16).float(), atol=1.6e-2, rtol=1.6e-2, msg='slab')
+  assert (got[..., :col0] == 5).all() and (got[..., col0 + ncols:] == 0).all()
+  ref_edw = om * torch.clamp((n_pred * -vt[:, None, :]).sum(-1), max=0.0) ** 2 + pm * (1.0 - (n_den * n_pred).sum(-1))
+  close(edw.cpu().view(B, S), ref_edw.detach(), atol=1e-9, rtol=1e-4, msg='extra_dw')
+  # backward
+  d_slab = torch.zeros(M, ld, dtype=torch.bfloat16, device='cuda')
+  d_slab[:, col0:col0 + ncols] = g_slab.reshape(M, ncols).to(torch.bfloat16).cuda()
+  d_gp, d_rr, d_rgd = torch.empty(M, 3, device='cuda'), torch.empty(M, device='cuda'), torch.empty(3, M, device='cuda')
+  stats = torch.zeros(8, device='cuda')
+  drd = torch.tensor(rng.normal(size=M).astype(np.float32)).cuda()
+  ddf = torch.tensor(rng.normal(size=(M, 3)).astype(np.float32)).cuda()
+  ops.refdir_bwd(desc, mat_d, ml_d, gp_c, rr_c, rgd_c, vt.cuda(), w.reshape(M).contiguous().cuda(), d_slab, om, pm,
+                 True, drd, ddf, None, d_gp, d_rr, d_rgd, stats)
+  torch.cuda.synchronize()
+  for got_, ref, name in [(d_gp.cpu().view(B, S, 3), grads[0], 'd grad_pred'),
+                          (d_rr.cpu().view(B, S, 1), grads[1], 'd raw_rough'),
+                          (d_rgd.cpu().view(3, B, S), grads[2], 'd raw_grad_density')]:
+    close(got_, ref, atol=2e-4 * float(ref.abs().max()) + 1e-9, rtol=2e-3, msg=name)
+  close(stats[4].cpu(), l_or.detach(), rtol=1e-4, atol=1e-9, msg='orientation loss')
+  close(stats[5].cpu(), l_pn.detach(), rtol=1e-4, atol=1e-9, msg='pred-normal loss')
+  hs = d_slab.float().cpu()[:, col0:col0 + 11]
+  close(hs[:, 0], drd.cpu().to(torch.bfloat16).float(), atol=0, rtol=0, msg='head slab density')
+  close(hs[:, 1:4], d_gp.cpu().to(torch.bfloat16).float(), atol=0, rtol=0, msg='head slab grad_pred')
+  close(hs[:, 4:7], ddf.cpu().to(torch.bfloat16).float(), atol=0, rtol=0, msg='head slab diffuse')
+  assert (hs[:, 7:10] == 0).all()
+  close(hs[:, 10], d_rr.cpu().to(torch.bfloat16).float(), atol=0, rtol=0, msg='head slab roughness')
+
+
+def test_outer_mask_and_gemm_mask_mod_addend(ops):
+  from multinerf_b200 import lib as L
+  rng = np.random.default_rng(51)
+  M, N, K = 256, 128, 192
+  bits = torch.tensor(rng.integers(-2 ** 31, 2 ** 31, (M, N // 32)), dtype=torch.int32)
+  maskb = ((bits.long()[:, :, None] >> torch.arange(32)) & 1).reshape(M, N).bool()
+  rowv = torch.tensor(rng.normal(size=3 * M).astype(np.float32))
+  colv = torch.tensor(rng.normal(size=N).astype(np.float32))
+  out = torch.empty(3 * M, N, dtype=torch.bfloat16, device='cuda')
+  ops.outer_mask(rowv.cuda(), colv.cuda(), bits.cuda(), out, rows=3 * M, n=N, mask_mod=M)
+  ref = (rowv[:, None] * colv[None, :]) * maskb.repeat(3, 1)
+  close(out.float(), ref.to(torch.bfloat16).float(), atol=0, rtol=0, msg='outer_mask')
+  for impl in [1, 0]:
+    a = _bf(rng.normal(size=(3 * M, K)).astype(np.float32))
+    w = _bf(rng.normal(size=(N, K)).astype(np.float32) / math.sqrt(K))
+    add = _bf(rng.normal(size=(3 * M, N)).astype(np.float32))
+    o2 = torch.empty(3 * M, N, dtype=torch.bfloat16, device='cuda')
+    ops.gemm(L.GEMM_DGRAD, a.cuda(), w.cuda(), o2, m=3 * M, n=N, k=K, maskbits=bits.cuda(), mask_mod=M,
+             addend=add.cuda(), impl=impl)
+    ref2 = (a.float() @ w.float().T) * maskb.repeat(3, 1) + add.float()
+    close(o2.float(), ref2.to(torch.bfloat16).float(), atol=3e-2, rtol=1.6e-2, msg=f'mask_mod+addend impl={impl}')
+
+
+def test_encode_tangent_features(ops):
+  """d(IPE feature)/d(mean) against torch autograd of the oracle (no contraction)."""
+  from multinerf_b200 import geopoly
+  rng = np.random.default_rng(61)
+  B, S, maxdeg = 40, 16, 16
+  o, d, radii = _rays(rng, B)
+  o = o * 3
+  sdist = torch.tensor(np.sort(rng.uniform(0, 1, (B, S + 1)).astype(np.float32), -1))
+  nearv, farv = torch.full((B, 1), 2.0), torch.full((B, 1), 6.0)
+  basis = torch.tensor(geopoly.generate_basis('octahedron', 1), dtype=torch.float32)
+  _, s_to_t = o_coord.construct_ray_warps(None, nearv, farv)
+  means, covs = o_render.cast_rays(s_to_t(sdist), o, d, radii, 'cone', diag=False)
+  means = means.detach().requires_grad_(True)
+  lm, lv = o_coord.lift_and_diagonalize(means, covs, basis.T.contiguous())
+  enc = o_coord.integrated_pos_enc(lm, lv, 0, maxdeg)          # [B,S,F]
+  F = enc.shape[-1]
+  jac = torch.stack([torch.autograd.grad(enc[..., f].sum(), means, retain_graph=True)[0] for f in range(F)], -1)
+  M = B * S
+  feat = torch.empty(M, 128, dtype=torch.bfloat16, device='cuda')
+  tfeat = torch.empty(3 * M, 128, dtype=torch.bfloat16, device='cuda')
+  ops.encode(sdist.cuda(), o.cuda(), d.cuda(), radii[:, 0].contiguous().cuda(), nearv[:, 0].contiguous().cuda(),
+             farv[:, 0].contiguous().cuda(), basis.cuda(), min_deg=0, max_deg=maxdeg, feat=feat, feat_cols=128,
+             tfeat=tfeat)
+  got = tfeat.float().cpu().view(3, B, S, 128)[..., :F]          # [dir, B, S, F]
+  ref = jac.permute(2, 0, 1, 3)                                  # [3, B, S, F]
+  scale = float(ref.abs().max())
+  assert float(((got - ref).abs() > 1e-2 * ref.abs() + 2e-4 * scale).float().mean()) < 2e-3
+  close(feat.float().cpu().view(B, S, 128)[..., :F], enc.detach().to(torch.bfloat16).float(), atol=8e-3, rtol=0,
+        msg='features unchanged')

@@ -290,3 +290,89 @@ def test_rawnerf_train_step_vs_oracle(mods):
     rel = float((a - b).norm() / b.norm().clamp(min=1e-12))
     cos = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
     assert rel < 0.15 and cos > 0.99, (lname, rel, cos)
+
+
+def mini_refnerf():
+  from multinerf_b200 import configs
+  b = configs.Bundle()
+  c, m, n = b.config, b.model, b.nerf_mlp
+  c.data_loss_type, c.distortion_loss_mult, c.interlevel_loss_mult, c.data_coarse_loss_mult = 'mse', 0.0, 0.0, 0.1
+  c.orientation_loss_mult, c.orientation_coarse_loss_mult = 0.1, 0.01
+  c.predicted_normal_loss_mult, c.predicted_normal_coarse_loss_mult = 3e-4, 3e-5
+  c.adam_eps, c.near, c.far = 1e-8, 2.0, 6.0
+  m.num_levels, m.single_mlp, m.num_prop_samples, m.num_nerf_samples = 2, True, 16, 16
+  m.anneal_slope, m.dilation_multiplier, m.dilation_bias, m.single_jitter, m.resample_padding = 0., 0., 0., False, 0.01
+  n.net_depth, n.net_width, n.net_depth_viewdirs, n.net_width_viewdirs = 6, 128, 6, 64
+  n.basis_shape, n.basis_subdivisions, n.disable_density_normals, n.enable_pred_normals = 'octahedron', 1, False, True
+  n.use_directional_enc = n.use_reflections = n.enable_pred_roughness = True
+  n.use_diffuse_color = n.use_specular_tint = n.use_n_dot_v = True
+  n.deg_view, n.bottleneck_width, n.density_bias, n.max_deg_point = 5, 64, 0.5, 16
+  return b
+
+
+def test_refnerf_forward_and_train_step_vs_oracle(mods):
+  """BASELINE config 3 (blender_refnerf.gin) at reduced size: IDE of reflected directions, predicted
+  and density-gradient normals (forward-mode tangent chain), diffuse + tinted specular colour,
+  n.v, 6-layer view MLP with a skip connection, orientation + predicted-normal losses."""
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  bundle = mini_refnerf()
+  bundle.config.grad_max_norm = 0.0
+  B, S = 96, 16
+  rays, rng = synth_rays(7, B, 2.0, 6.0, unit_cube=False)
+  target = rng.uniform(0, 1, (B, 3)).astype(np.float32)
+  model, variables = models.construct_model(9, rays, bundle)
+  params0 = torch_tree(model.export_flax())
+  bases = {'nerf': model.plans['NerfMLP_0'].basis, 'prop': model.plans['NerfMLP_0'].basis}
+  rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, S)).astype(np.float32)) for _ in range(2)]}
+  orays = oracle_rays(rays)
+  # ---- forward (sample positions pinned to the oracle's per level)
+  rend_o, hist_o = o_models.model_apply(params0, bundle, bases, orays, 0.5, True, rand=rand, bf16=True)
+  rend_o = [{k: v.detach() for k, v in r.items()} for r in rend_o]
+  hist_o = [{k: (v.detach() if v is not None else None) for k, v in h.items()} for h in hist_o]
+  r = model._prep_rays(rays)
+  from multinerf_b200 import ops
+  states = model.forward_levels(rand, r, 0.5, True, True)
+  for i, st in enumerate(states):
+    st.sdist.copy_(hist_o[i]['sdist'].cuda())
+    model._mlp_forward(st, model.mlps[st.mname], r)
+    comp = ops.composite_fwd(st.raw_density, st.raw_rgb, st.sdist, r.directions, r.near_flat, r.far_flat,
+                             cfg=st.comp_cfg, raw_diffuse=st.heads.get('diffuse'), raw_tint=st.heads.get('tint'),
+                             want_samples=True, want_extras=True)
+    torch.cuda.synchronize()
+    err = (comp['density'].cpu() - hist_o[i]['density']).abs() / (1.0 + hist_o[i]['density'].abs())
+    assert float(err.max()) < 0.08 and float(err.mean()) < 4e-3, (i, float(err.max()), float(err.mean()))
+    close(st.normals_pred.cpu().view(B, S, 3), hist_o[i]['normals_pred'], atol=3e-2, rtol=0, msg='normals_pred')
+    # density normals: bf16 tangent chain vs fp32 autograd of the bf16-emulated forward
+    cosn = (st.normals.cpu().view(B, S, 3) * hist_o[i]['normals']).sum(-1)
+    assert float((cosn > 0.98).float().mean()) > 0.97, float((cosn > 0.98).float().mean())
+    close(st.roughness.cpu().view(B, S, 1), hist_o[i]['roughness'], atol=2e-2, rtol=0, msg='roughness')
+    close(comp['rgb_samples'], hist_o[i]['rgb'], atol=4e-2, rtol=0, msg=f'rgb samples level {i}')
+    close(comp['rgb'], rend_o[i]['rgb'], atol=1.5e-2, rtol=0, msg=f'pixel level {i}')
+  rend, hist = model(rand, rays, 0.5, True)
+  for k in ['normals', 'normals_pred', 'roughness']:
+    assert k in rend[-1] and hist[-1][k] is not None
+  close(rend[-1]['rgb'], rend_o[-1]['rgb'], atol=3e-2, rtol=0, msg='final pixel end-to-end')
+  # ---- one train step
+  opt0 = {'count': 0, 'mu': {}, 'nu': {}}
+  new_o, opt_o, stats_o, grads_o = o_train.train_step(params0, opt0, bundle, bases, orays, torch.tensor(target), 0.5,
+                                                      rand=rand, bf16=True)
+  step_fn = train_utils.create_train_step(model, bundle.config)
+  state = train_utils.TrainState(variables)
+  state, stats, _ = step_fn(rand, state, utils.Batch(rays=rays, rgb=target), None, 0.5)
+  torch.cuda.synchronize()
+  stats.materialize()
+  close(stats['mses'], stats_o['mses'].detach(), atol=2e-3, rtol=3e-2, msg='mses')
+  for k in ['orientation', 'predicted_normals']:
+    lo = float(stats_o['losses'][k].detach())
+    assert abs(stats['losses'][k] - lo) < 0.05 * abs(lo) + 1e-7, (k, stats['losses'][k], lo)
+  g = model.export_grads_flax()
+  report = {}
+  for lname in g['NerfMLP_0']:
+    a = torch.tensor(g['NerfMLP_0'][lname]['kernel']).double().flatten()
+    b = grads_o[('NerfMLP_0', lname, 'kernel')].double().flatten()
+    rel = float((a - b).norm() / b.norm().clamp(min=1e-12))
+    cos = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+    report[lname] = (round(rel, 3), round(cos, 4))
+  bad = {k: v for k, v in report.items() if not (v[0] < 0.2 and v[1] > 0.98)}
+  assert not bad, (bad, report)

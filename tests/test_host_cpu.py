@@ -99,9 +99,19 @@ def test_layer_tables_reproduce_published_param_counts():
   bb = configs.bundle_blender_256()
   assert MLPPlan(bb.nerf_mlp).num_params + MLPPlan(bb.prop_mlp).num_params == 835205
   with pytest.raises(NotImplementedError):
-    bb.nerf_mlp.use_reflections = True
-    bb.nerf_mlp.enable_pred_normals = True
+    bb.nerf_mlp.bottleneck_noise = 0.1
     MLPPlan(bb.nerf_mlp)
+  # blender_refnerf.gin: 713,230 (scripts/generate_tables.ipynb Ref-NeRF row) and its layer order
+  ref = configs.Bundle()
+  n = ref.nerf_mlp
+  n.net_depth_viewdirs, n.basis_shape, n.basis_subdivisions, n.disable_density_normals = 8, 'octahedron', 1, False
+  n.enable_pred_normals = n.use_directional_enc = n.use_reflections = n.enable_pred_roughness = True
+  n.use_diffuse_color = n.use_specular_tint = n.use_n_dot_v = True
+  n.deg_view, n.bottleneck_width, n.density_bias, n.max_deg_point = 5, 128, 0.5, 16
+  rp = MLPPlan(n)
+  assert rp.num_params == 713230
+  assert [sp.role for sp in rp.specs[8:14]] == ['density', 'grad_pred', 'diffuse', 'tint', 'roughness', 'bottleneck']
+  assert (rp.vin_dim, rp.vin_pad, rp.view_concat_after) == (201, 256, [4]) and rp.specs[19].in_dim == 329
 
 
 def test_level_schedule_matches_reference_constants():
