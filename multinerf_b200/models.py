@@ -55,8 +55,6 @@ class MLPPlan:
     if cfg.net_activation != 'relu' or cfg.density_activation != 'softplus' or \
        cfg.roughness_activation != 'softplus':
       raise NotImplementedError('CUDA path supports relu trunk / softplus density and roughness')
-    if cfg.bottleneck_noise > 0:
-      raise NotImplementedError('bottleneck_noise is not wired into the CUDA path yet')
     if cfg.num_rgb_channels != 3:
       raise NotImplementedError('num_rgb_channels != 3')
     self.cfg = cfg
@@ -281,8 +279,6 @@ class Model:
       setattr(self, f.name, getattr(m, f.name))
     if m.num_glo_features > 0:
       raise NotImplementedError('GLO embeddings are not wired into the CUDA path yet')
-    if m.bg_intensity_range[0] != m.bg_intensity_range[1]:
-      raise NotImplementedError('random background colours are not wired into the CUDA path yet')
     if m.ray_shape not in L.RAY_SHAPE:
       raise ValueError("ray_shape must be 'cone' or 'cylinder'")
     if m.raydist_fn not in L.RAYDIST:
@@ -534,6 +530,9 @@ class Model:
     bt = plan.one('bottleneck')
     ops.gemm(L.GEMM_FWD, x, mlp.w_nk[bt.name], st.vin[:, :bt.out_dim], m=M, n=bt.out_dim,
              k=bt.in_pad, act=L.ACT_NONE, bias=mlp.b(bt), impl=impl)
+    if cfg.bottleneck_noise > 0 and getattr(st, 'bneck_noise', None) is not None:
+      # models.py:529-533 (regulariser, unused by the shipped configs): plain elementwise add
+      st.vin[:, :bt.out_dim].add_((cfg.bottleneck_noise * st.bneck_noise).to(torch.bfloat16))
     if plan.ref_stage:
       desc = self._refdir_desc(st, plan)
       desc.ld = st.vin.stride(0)
@@ -615,6 +614,13 @@ class Model:
                        use_dilation=lv['use_dilation'], domain=(s_near, s_far), anneal=lv['anneal'],
                        resample_padding=m.resample_padding, jitter=jit, single_jitter=m.single_jitter,
                        u_base=u_base, max_jitter=max_jitter, out=st.sdist, anneal_dev=anneal_dev)
+      st.bneck_noise = None
+      if mlp.plan.cfg.bottleneck_noise > 0 and rng is not None and mlp.plan.has_rgb:
+        bwid = mlp.plan.cfg.bottleneck_width
+        if isinstance(rng, dict):
+          st.bneck_noise = rng['bottleneck_noise'][i].to(dev).reshape(B * lv['S'], bwid)
+        else:
+          st.bneck_noise = torch.randn(B * lv['S'], bwid, device=dev, generator=rng)
       st.loss_mults = self.level_loss_mults(loss_config, i, B) if (loss_config is not None and
                                                                    mlp.plan.ref_stage) else None
       if st.loss_mults is not None:
@@ -632,9 +638,22 @@ class Model:
         else:
           st.noise = torch.randn(B, lv['S'], device=dev, generator=rng)
       st.comp_cfg = self._comp_cfg(mlp.plan.cfg)
+      # background colour (models.py:240-254): constant, midpoint (rng=None) or per-ray uniform draws
+      lo, hi = m.bg_intensity_range
+      st.bg_rgb = None
+      if lo != hi:
+        if rng is None:
+          st.comp_cfg['bg_const'] = (lo + hi) / 2
+        else:
+          if isinstance(rng, dict):
+            ub = rng['bg'][i].to(dev).reshape(B, 3)
+          else:
+            ub = torch.rand(B, 3, device=dev, generator=rng)
+          st.bg_rgb = (lo + (hi - lo) * ub).contiguous()
       st.comp = ops.composite_fwd(st.raw_density, st.raw_rgb, st.sdist, rays.directions,
                                   rays.near_flat, rays.far_flat, cfg=st.comp_cfg,
-                                  density_noise=st.noise, rgb_scale=rgb_scale if st.raw_rgb is not None else None,
+                                  density_noise=st.noise, bg_rgb=st.bg_rgb,
+                                  rgb_scale=rgb_scale if st.raw_rgb is not None else None,
                                   raw_diffuse=st.heads.get('diffuse'), raw_tint=st.heads.get('tint'),
                                   want_samples=want_samples, want_extras=compute_extras)
       st.rgb_scale = rgb_scale if st.raw_rgb is not None else None

@@ -73,10 +73,17 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
   mcfg = model.mcfg
   if config.data_loss_type not in ('mse', 'charb', 'rawnerf'):
     raise NotImplementedError(f'data_loss_type {config.data_loss_type!r}')
-  if config.weight_decay_mults:
-    raise NotImplementedError('weight_decay_mults')
-  if use_graph and mcfg.near_anneal_rate is not None:
-    use_graph = False          # init_s_near depends on train_frac by value
+  if use_graph and (mcfg.near_anneal_rate is not None or
+                    mcfg.bg_intensity_range[0] != mcfg.bg_intensity_range[1] or
+                    any(p.cfg.bottleneck_noise > 0 for p in model.plans.values())):
+    use_graph = False          # init_s_near by value / extra random draws: stay eager
+  # weight decay (train_utils.py:304-309): 'Module' or 'Module/Dense_k' -> multiplier on ||.||^2
+  decay_views = []
+  for key, mult in dict(config.weight_decay_mults).items():
+    parts = key.split('/')
+    if parts[0] not in model.plans or len(parts) > 2:
+      raise ValueError(f'weight_decay_mults: unknown parameter subtree {key!r}')
+    decay_views.append((parts[0], parts[1] if len(parts) == 2 else None, float(mult)))
   dev = model.device
   stats_buf = torch.zeros(mcfg.num_levels, 8, device=dev)
   scratch = torch.zeros(4, device=dev)
@@ -112,7 +119,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
           interlevel_mult=0.0 if is_fine else config.interlevel_loss_mult,
           sdist_fine=None if is_fine else fine.sdist,
           weights_fine=None if is_fine else fine.comp['weights'],
-          density_noise=st.noise, rgb_scale=st.rgb_scale, d_raw_density=st.d_raw_density,
+          density_noise=st.noise, bg_rgb=st.bg_rgb, rgb_scale=st.rgb_scale, d_raw_density=st.d_raw_density,
           d_raw_rgb=st.d_raw_rgb, d_rgb_scale=_d_scale_buf(st),
           raw_diffuse=st.heads.get('diffuse'), raw_tint=st.heads.get('tint'),
           extra_dw=st.extra_dw if st.loss_mults is not None else None,
@@ -124,6 +131,19 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
         params.seg('exposure_scaling_offsets', params.grads).view(-1, 3).index_add_(0, eidx, g)
       model._mlp_backward(st, model.mlps[st.mname], rays=rays, impl=impl, loss_mults=st.loss_mults,
                           stats=stats_buf[i])
+    if decay_views:
+      weight_decay()
+
+  def weight_decay():
+    # loss += mult * sum(w^2)  ->  grad += 2 mult w ; the loss value goes to stats row 0, slot 6
+    params = model.params
+    for mname, lname, mult in decay_views:
+      mlp = model.mlps[mname]
+      for sp in mlp.plan.specs:
+        if lname is None or sp.name == lname:
+          for view_p, view_g in ((mlp.W(sp), mlp.W(sp, mlp.grads)), (mlp.b(sp), mlp.b(sp, mlp.grads))):
+            view_g.add_(view_p, alpha=2.0 * mult)
+            stats_buf[0, 6] += mult * (view_p * view_p).sum()
 
   def _d_scale_buf(st):
     if st.rgb_scale is None:
@@ -255,6 +275,8 @@ class LazyStats(dict):
     losses = {'data': float(b[:, 0].sum()), 'interlevel': float(b[:, 3].sum()),
               'distortion': float(b[:, 2].sum()), 'orientation': float(b[:, 4].sum()),
               'predicted_normals': float(b[:, 5].sum())}
+    if float(b[:, 6].abs().sum()) > 0:
+      losses['weight'] = float(b[:, 6].sum())
     self.update(mses=mses, psnrs=-10.0 / math.log(10.0) * torch.log(mses), losses=losses,
                 loss=sum(losses.values()))
     self['psnr'] = float(self['psnrs'][-1])

@@ -109,6 +109,19 @@ def loss_fn(params, bundle, bases, rays, batch_rgb, train_frac, rand=None, bf16=
   if config.predicted_normal_coarse_loss_mult > 0 or config.predicted_normal_loss_mult > 0:
     losses['predicted_normals'] = predicted_normal_loss(bundle.model.num_levels, ray_history,
                                                         config)
+  if getattr(config, 'weight_decay_mults', None):
+    # train_utils.py:304-309: keys 'Module', 'Module/Dense_k' (or 'Module/Dense_k/kernel')
+    def norm_sq(tree):
+      if isinstance(tree, dict):
+        return sum(norm_sq(v) for v in tree.values())
+      return (tree ** 2).sum()
+    total = 0.0
+    for key, mult in dict(config.weight_decay_mults).items():
+      sub = params
+      for part in key.split('/'):
+        sub = sub[part]
+      total = total + mult * norm_sq(sub)
+    losses['weight'] = total
   stats['losses'] = losses
   stats['loss'] = sum(losses.values())
   return stats['loss'], stats, (renderings, ray_history)

@@ -376,3 +376,43 @@ def test_refnerf_forward_and_train_step_vs_oracle(mods):
     report[lname] = (round(rel, 3), round(cos, 4))
   bad = {k: v for k, v in report.items() if not (v[0] < 0.2 and v[1] > 0.98)}
   assert not bad, (bad, report)
+
+
+def test_weight_decay_random_background_and_bottleneck_noise(mods):
+  """Smaller switches of the path: weight_decay_mults (train_utils.py:304-309), random background
+  colours (models.py:240-254) and bottleneck noise (models.py:529-533) against the oracle."""
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  bundle = mini360()
+  bundle.config.grad_max_norm = 0.0
+  bundle.config.weight_decay_mults = {'NerfMLP_0': 1e-3, 'PropMLP_0/Dense_0': 1e-2}
+  bundle.model.bg_intensity_range = (0.2, 0.9)
+  bundle.nerf_mlp.bottleneck_noise = 0.3
+  B = 128
+  rays, rng = synth_rays(13, B, 0.2, 1e6)
+  target = rng.uniform(0, 1, (B, 3)).astype(np.float32)
+  model, variables = models.construct_model(14, rays, bundle)
+  params0 = torch_tree(model.export_flax())
+  bases = {'nerf': model.plans['NerfMLP_0'].basis, 'prop': model.plans['PropMLP_0'].basis}
+  S = [32, 32, 16]
+  rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, 1)).astype(np.float32)) for _ in S],
+          'bg': [torch.tensor(rng.uniform(0, 1, (B, 3)).astype(np.float32)) for _ in S],
+          'bottleneck_noise': [torch.tensor(rng.normal(size=(B, s, 64)).astype(np.float32)) for s in S]}
+  # deterministic render: midpoint background
+  rend_o, _ = o_models.model_apply(params0, bundle, bases, oracle_rays(rays), 0.5, False, rand=None, bf16=True)
+  rend, _ = model(None, rays, 0.5, False)
+  close(rend[0]['rgb'], rend_o[0]['rgb'].detach(), atol=1e-2, rtol=0, msg='midpoint background')
+  opt0 = {'count': 0, 'mu': {}, 'nu': {}}
+  new_o, opt_o, stats_o, grads_o = o_train.train_step(params0, opt0, bundle, bases, oracle_rays(rays),
+                                                      torch.tensor(target), 0.5, rand=rand, bf16=True)
+  step_fn = train_utils.create_train_step(model, bundle.config, use_graph=True)   # falls back to eager
+  state = train_utils.TrainState(variables)
+  state, stats, _ = step_fn(rand, state, utils.Batch(rays=rays, rgb=target), None, 0.5)
+  torch.cuda.synchronize()
+  stats.materialize()
+  close(stats['mses'], stats_o['mses'].detach(), atol=3e-3, rtol=3e-2, msg='mses (random bg)')
+  g = model.export_grads_flax()
+  for mname, lname in [('NerfMLP_0', 'Dense_3'), ('PropMLP_0', 'Dense_0'), ('PropMLP_0', 'Dense_1')]:
+    a = torch.tensor(g[mname][lname]['kernel']).double().flatten()
+    b = grads_o[(mname, lname, 'kernel')].double().flatten()
+    assert float((a - b).norm() / b.norm()) < 0.15, (mname, lname, float((a - b).norm() / b.norm()))
