@@ -99,7 +99,7 @@ def test_layer_tables_reproduce_published_param_counts():
   bb = configs.bundle_blender_256()
   assert MLPPlan(bb.nerf_mlp).num_params + MLPPlan(bb.prop_mlp).num_params == 835205
   with pytest.raises(NotImplementedError):
-    bb.nerf_mlp.bottleneck_noise = 0.1
+    bb.nerf_mlp.net_activation = 'silu'          # only the ReLU trunk has a CUDA path
     MLPPlan(bb.nerf_mlp)
   # blender_refnerf.gin: 713,230 (scripts/generate_tables.ipynb Ref-NeRF row) and its layer order
   ref = configs.Bundle()
