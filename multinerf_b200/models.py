@@ -50,8 +50,9 @@ class MLPPlan:
   HEAD_SLOTS = {'density': (0, 1), 'grad_pred': (1, 3), 'diffuse': (4, 3), 'tint': (7, 3),
                 'roughness': (10, 1)}     # column slots of the head-gradient slab (csrc/refnerf.cu)
 
-  def __init__(self, cfg: configs.MLPConfig, use_viewdirs=True):
+  def __init__(self, cfg: configs.MLPConfig, use_viewdirs=True, glo_features=0):
     cfg.validate()
+    self.glo_features = glo_features
     if cfg.net_activation != 'relu' or cfg.density_activation != 'softplus' or \
        cfg.roughness_activation != 'softplus':
       raise NotImplementedError('CUDA path supports relu trunk / softplus density and roughness')
@@ -122,7 +123,8 @@ class MLPPlan:
         self.dir_dim = ref_utils.ide_dim(cfg.deg_view)
       else:
         self.dir_dim = 3 + 6 * cfg.deg_view
-      vin = bw + self.dir_dim + (1 if cfg.use_n_dot_v else 0)
+      self.glo_col0 = bw + self.dir_dim + (1 if cfg.use_n_dot_v else 0)
+      vin = self.glo_col0 + glo_features            # [bottleneck | dir enc | n.v | GLO] (models.py:556-572)
       vin_pad = _pad64(vin)
       if self.ref_stage and vin_pad - bw < 11:
         vin_pad += 64
@@ -277,15 +279,15 @@ class Model:
     self.device = torch.device(device if device is not None else torch.device('cuda', torch.cuda.current_device()))
     for f in dataclasses.fields(m):            # expose Model.<field> like the reference
       setattr(self, f.name, getattr(m, f.name))
-    if m.num_glo_features > 0:
-      raise NotImplementedError('GLO embeddings are not wired into the CUDA path yet')
+    if m.num_glo_features > 0 and m.single_mlp:
+      raise ValueError('GLO with single_mlp feeds two input widths to the same view MLP (flax would reject it)')
     if m.ray_shape not in L.RAY_SHAPE:
       raise ValueError("ray_shape must be 'cone' or 'cylinder'")
     if m.raydist_fn not in L.RAYDIST:
       raise ValueError(f'raydist_fn {m.raydist_fn!r} not supported')
     if not m.stop_level_grad:
       raise NotImplementedError('stop_level_grad=False (gradients through resampling)')
-    self.plans = {'NerfMLP_0': MLPPlan(bundle.nerf_mlp, m.use_viewdirs)}
+    self.plans = {'NerfMLP_0': MLPPlan(bundle.nerf_mlp, m.use_viewdirs, glo_features=m.num_glo_features)}
     if not m.single_mlp:
       self.plans['PropMLP_0'] = MLPPlan(bundle.prop_mlp, m.use_viewdirs)
     for pname, plan in self.plans.items():
@@ -296,6 +298,8 @@ class Model:
     self.extra_params = {}
     if m.learned_exposure_scaling:
       self.extra_params['exposure_scaling_offsets'] = m.num_glo_embeddings * 3   # Embed [N,3], zeros
+    if m.num_glo_features > 0:
+      self.extra_params['Embed_0'] = m.num_glo_embeddings * m.num_glo_features    # GLO vectors
     self.params: Optional[Params] = None
     self.mlps: Dict[str, MLPDevice] = {}
     self._levels: Dict[Any, LevelState] = {}
@@ -331,6 +335,10 @@ class Model:
         if name in flax_params:
           o, n = params.offsets[name]
           host[o:o + n] = np.asarray(flax_params[name]['embedding'], np.float32).reshape(-1)
+    elif 'Embed_0' in self.extra_params:
+      # flax nn.Embed default init: variance_scaling(1.0, 'fan_in', 'normal', out_axis=0)
+      o, n = params.offsets['Embed_0']
+      host[o:o + n] = rng.standard_normal(n).astype(np.float32) / math.sqrt(self.mcfg.num_glo_features)
     params.flat.copy_(torch.from_numpy(host))
     self.bind(params)
     return params
@@ -351,7 +359,8 @@ class Model:
         rows = s.row_map if s.row_map is not None else np.arange(s.in_dim)
         out[mname][s.name] = {'kernel': Wp[rows].copy(), 'bias': mlp.b(s).detach().cpu().numpy().copy()}
     for name in self.extra_params:
-      out[name] = {'embedding': self.params.seg(name).detach().cpu().numpy().reshape(-1, 3).copy()}
+      out[name] = {'embedding': self.params.seg(name).detach().cpu().numpy().reshape(
+          self.mcfg.num_glo_embeddings, -1).copy()}
     return out
 
   def export_grads_flax(self):
@@ -365,7 +374,8 @@ class Model:
         out[mname][s.name] = {'kernel': Wp[rows].copy(),
                               'bias': mlp.b(s, mlp.grads).detach().cpu().numpy().copy()}
     for name in self.extra_params:
-      out[name] = {'embedding': self.params.seg(name, self.params.grads).detach().cpu().numpy().reshape(-1, 3).copy()}
+      out[name] = {'embedding': self.params.seg(name, self.params.grads).detach().cpu().numpy().reshape(
+          self.mcfg.num_glo_embeddings, -1).copy()}
     return out
 
   # ------------------------------------------------------------------ schedule
@@ -483,6 +493,8 @@ class Model:
         use_roughness=cfg.enable_pred_roughness, deg_view=cfg.deg_view, ide_n=ide_n,
         roughness_bias=cfg.roughness_bias, ld=0, col0=bw, col_end=plan.vin_pad)
 
+  # NB: with GLO the slab's zero-fill would also clear the GLO columns; they are written after it.
+
   # ------------------------------------------------------------------ forward
   def _mlp_forward(self, st: LevelState, mlp: MLPDevice, rays, impl=0, loss_mults=None):
     """loss_mults = (orientation, predicted-normal) multipliers of this level divided by the number
@@ -544,6 +556,12 @@ class Model:
                      st.extra_dw if loss_mults is not None else None)
     else:
       ops.viewdir_enc(rays.viewdirs, S, cfg.deg_view, st.vin, bt.out_dim, plan.vin_pad)
+    if plan.glo_features > 0:
+      # GLO vector of the ray's camera, broadcast over the samples (models.py:565-569)
+      g0 = plan.glo_col0
+      st.vin.view(B, S, st.vin.stride(0))[:, :, g0:g0 + plan.glo_features] = \
+          (st.glo_vec if st.glo_vec is not None else torch.zeros(B, plan.glo_features, device=st.vin.device)
+           )[:, None, :].to(torch.bfloat16)
     v = st.vin
     for i, sp in enumerate(plan.by_role('view')):
       Wv = sp.out_dim
@@ -572,7 +590,7 @@ class Model:
     return om / B, pm / B, config.orientation_loss_target == 'normals_pred'
 
   def forward_levels(self, rng, rays, train_frac, compute_extras, want_samples, impl=0, anneal_dev=None,
-                     loss_config=None):
+                     loss_config=None, zero_glo=True):
     """Runs all levels; returns the list of LevelState (buffers stay valid until the next call)."""
     if self.params is None:
       raise RuntimeError('Model has no parameters: call construct_model()/init() first')
@@ -614,6 +632,9 @@ class Model:
                        use_dilation=lv['use_dilation'], domain=(s_near, s_far), anneal=lv['anneal'],
                        resample_padding=m.resample_padding, jitter=jit, single_jitter=m.single_jitter,
                        u_base=u_base, max_jitter=max_jitter, out=st.sdist, anneal_dev=anneal_dev)
+      st.glo_vec = None
+      if m.num_glo_features > 0 and not lv['is_prop'] and not zero_glo:
+        st.glo_vec = self.params.seg('Embed_0').view(m.num_glo_embeddings, -1)[rays.cam_idx[:, 0].long()]
       st.bneck_noise = None
       if mlp.plan.cfg.bottleneck_noise > 0 and rng is not None and mlp.plan.has_rgb:
         bwid = mlp.plan.cfg.bottleneck_width
@@ -665,7 +686,7 @@ class Model:
     """models.py:75-312.  rng: None (deterministic), a torch.Generator on the device, or a
     dict of explicit draws {'jitter': [per level], 'density_noise': [per level]}."""
     r = self._prep_rays(rays)
-    states = self.forward_levels(rng, r, train_frac, compute_extras, want_samples=True)
+    states = self.forward_levels(rng, r, train_frac, compute_extras, want_samples=True, zero_glo=zero_glo)
     lead = tuple(np.asarray(rays.origins).shape[:-1]) if not isinstance(rays.origins, torch.Tensor) \
         else tuple(rays.origins.shape[:-1])
     renderings, ray_history = [], []
@@ -769,6 +790,10 @@ class Model:
                  addend=sc.d_vin_skip if have_skip_grad else None, impl=impl)
         # bias gradient of the bottleneck = column sums of d vin[:, :bw]
         ops.colsum(sc.d_vin[:, :bw], bw, mlp.b(bt, g))
+        d_glo_ref = None
+        if plan.glo_features > 0 and st.glo_vec is not None:     # before the slab columns are re-used
+          g0 = plan.glo_col0
+          d_glo_ref = sc.d_vin.view(st.B, st.S, plan.vin_pad)[:, :, g0:g0 + plan.glo_features].float().sum(1)
         desc = self._refdir_desc(st, plan)
         desc.ld = st.vin.stride(0)
         mat, ml, _ = mlp.ide_tables() if cfg.use_directional_enc else (None, None, 0)
@@ -791,8 +816,14 @@ class Model:
       else:
         dbott = sc.d_vin[:, :bw]
         # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
-        ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], dbott, m=M, n=bw, k=Wv,
-                 colsum=mlp.b(bt, g), addend=sc.d_vin_skip[:, :bw] if have_skip_grad else None, impl=impl)
+        if plan.glo_features > 0:
+          # the GLO columns of vin carry gradient too: full-width dgrad, then sum over the samples
+          ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], sc.d_vin, m=M, n=plan.vin_pad, k=Wv,
+                   addend=sc.d_vin_skip if have_skip_grad else None, impl=impl)
+          ops.colsum(dbott, bw, mlp.b(bt, g))
+        else:
+          ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], dbott, m=M, n=bw, k=Wv,
+                   colsum=mlp.b(bt, g), addend=sc.d_vin_skip[:, :bw] if have_skip_grad else None, impl=impl)
         ops.gemm(L.GEMM_WGRAD, x_last, dbott, mlp.W(bt, g), m=bt.in_pad, n=bw, k=M, impl=impl)
         # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
         ops.gemm(L.GEMM_DGRAD, dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bw,
@@ -800,6 +831,12 @@ class Model:
                  colsum=mlp.b(trunk[-1], g), impl=impl)
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=None, dw=mlp.W(d, g),
                    db=mlp.b(d, g))
+      if plan.glo_features > 0 and st.glo_vec is not None:
+        g0 = plan.glo_col0
+        d_glo = d_glo_ref if plan.ref_stage else \
+            sc.d_vin.view(st.B, st.S, plan.vin_pad)[:, :, g0:g0 + plan.glo_features].float().sum(1)
+        self.params.seg('Embed_0', self.params.grads).view(self.mcfg.num_glo_embeddings, -1).index_add_(
+            0, rays.cam_idx[:, 0].long(), d_glo)
     else:
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=dy, relu_mask=True,
                    dw=mlp.W(d, g), db=mlp.b(d, g), dxsum=mlp.b(trunk[-1], g))

@@ -104,7 +104,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     stats_buf.zero_()
     states = model.forward_levels(rng if config.randomized else None, rays, train_frac,
                                   compute_extras=False, want_samples=False, impl=impl,
-                                  anneal_dev=anneal_ptr, loss_config=config)
+                                  anneal_dev=anneal_ptr, loss_config=config, zero_glo=False)
     fine = states[-1]
     n = len(states)
     for i in range(n - 1, -1, -1):

@@ -416,3 +416,43 @@ def test_weight_decay_random_background_and_bottleneck_noise(mods):
     a = torch.tensor(g[mname][lname]['kernel']).double().flatten()
     b = grads_o[(mname, lname, 'kernel')].double().flatten()
     assert float((a - b).norm() / b.norm()) < 0.15, (mname, lname, float((a - b).norm() / b.norm()))
+
+
+def test_glo_embeddings_vs_oracle(mods):
+  """configs/360_glo4.gin at reduced size: per-camera GLO vectors appended to the view-MLP input
+  (models.py:101-110,565-569), their gradient scattered back into the embedding table."""
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  bundle = mini360()
+  bundle.config.grad_max_norm = 0.0
+  bundle.model.num_glo_features = 4
+  bundle.model.num_glo_embeddings = 16
+  B = 128
+  rays, rng = synth_rays(17, B, 0.2, 1e6)
+  rays.cam_idx = rng.integers(0, 16, (B, 1)).astype(np.int32)
+  target = rng.uniform(0, 1, (B, 3)).astype(np.float32)
+  model, variables = models.construct_model(18, rays, bundle)
+  params0 = torch_tree(model.export_flax())
+  assert params0['Embed_0']['embedding'].shape == (16, 4)
+  assert params0['NerfMLP_0']['Dense_10']['kernel'].shape[0] == 64 + 27 + 4
+  bases = {'nerf': model.plans['NerfMLP_0'].basis, 'prop': model.plans['PropMLP_0'].basis}
+  rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, 1)).astype(np.float32)) for _ in range(3)]}
+  orays = oracle_rays(rays)
+  orays.cam_idx = torch.tensor(rays.cam_idx)
+  # zero_glo=True (construct/eval default) vs False
+  for zero_glo in [True, False]:
+    rend_o, _ = o_models.model_apply(params0, bundle, bases, orays, 0.5, False, rand=rand, zero_glo=zero_glo, bf16=True)
+    rend, _ = model(rand, rays, 0.5, False, zero_glo=zero_glo)
+    close(rend[-1]['rgb'], rend_o[-1]['rgb'].detach(), atol=2e-2, rtol=0, msg=f'pixel zero_glo={zero_glo}')
+  opt0 = {'count': 0, 'mu': {}, 'nu': {}}
+  new_o, opt_o, stats_o, grads_o = o_train.train_step(params0, opt0, bundle, bases, orays, torch.tensor(target), 0.5,
+                                                      rand=rand, bf16=True)
+  step_fn = train_utils.create_train_step(model, bundle.config)
+  state = train_utils.TrainState(variables)
+  state, stats, _ = step_fn(rand, state, utils.Batch(rays=rays, rgb=target), None, 0.5)
+  torch.cuda.synchronize()
+  g = model.export_grads_flax()
+  a = torch.tensor(g['Embed_0']['embedding']).double().flatten()
+  b = grads_o[('Embed_0', 'embedding')].double().flatten()
+  rel = float((a - b).norm() / b.norm())
+  assert float(b.norm()) > 0 and rel < 0.15, rel
