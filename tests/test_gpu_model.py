@@ -434,7 +434,7 @@ def test_glo_embeddings_vs_oracle(mods):
   model, variables = models.construct_model(18, rays, bundle)
   params0 = torch_tree(model.export_flax())
   assert params0['Embed_0']['embedding'].shape == (16, 4)
-  assert params0['NerfMLP_0']['Dense_10']['kernel'].shape[0] == 64 + 27 + 4
+  assert params0['NerfMLP_0']['Dense_8']['kernel'].shape[0] == 64 + 27 + 4
   bases = {'nerf': model.plans['NerfMLP_0'].basis, 'prop': model.plans['PropMLP_0'].basis}
   rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, 1)).astype(np.float32)) for _ in range(3)]}
   orays = oracle_rays(rays)
