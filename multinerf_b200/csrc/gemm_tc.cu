@@ -4,12 +4,21 @@
 // 527,577 and the dgrad / wgrad GEMMs jax.value_and_grad derives from them
 // (train_utils.py:316-317).
 //
-//   warp 0   : TMA producer (one elected lane) -- cp.async.bulk.tensor.2d into a 4-stage ring
-//   warp 1   : MMA issuer  (one elected lane) -- tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256
+//   warp 0   : TMA producer (one elected lane) -- cp.async.bulk.tensor.2d into an operand ring
+//   warp 1   : MMA issuer  (one elected lane) -- tcgen05.mma.kind::f16, N<=256
 //   warp 2   : TMEM allocator (512 columns = two 256-column accumulator stages)
 //   warps 4-11: epilogue -- two warps per TMEM lane quadrant (each takes half of the tile's
 //              columns): tcgen05.ld 32x32b, bias/ReLU | mask/rank-1/column sums | fp32 reduction,
 //              swizzled smem staging + TMA bulk stores
+//
+// Two variants of the same kernel (template CTAS):
+//   CTAS=1 : one CTA per 128 x block_n tile, tcgen05.mma.cta_group::1 (M=128); any shape.
+//   CTAS=2 : a two-CTA cluster (one TPC) per 256 x 256 tile, tcgen05.mma.cta_group::2 (M=256) issued by
+//            the leader CTA; each CTA stages its own 128 A rows and HALF of the B tile, so operand
+//            shared-memory traffic per SM drops by a third and the ring holds 6 stages.  The leader's
+//            "full" barriers collect both CTAs' TMA bytes; "empty"/"accumulator full" arrivals are
+//            multicast to both CTAs by tcgen05.commit; both epilogues release the accumulator on the
+//            leader's barrier.  Used when M % 256 == 0 and block_n == 256 (all 360-config layers).
 //
 // Operand layouts (all bf16, 128-byte swizzle):
 //   FWD / DGRAD : A[M,K] and B[N,K] are K-major (reduction index contiguous);
@@ -17,6 +26,7 @@
 //                 out[Mo,N] += X^T dY, split over R with fp32 vector reductions.
 #include <cuda.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -29,15 +39,16 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
 constexpr int MAX_BLOCK_N = 256;
-constexpr int NUM_STAGES = 4;
 constexpr int NUM_ACC = 2;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KiB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int OUT_STAGE_BYTES = NUM_EPI_WARPS * 32 * 128;    // one 32-row x 128-byte slab per epilogue warp
-constexpr int NUM_OUT_STAGES = 1;
-constexpr int SMEM_BYTES = NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_OUT_STAGES * OUT_STAGE_BYTES +
-                           1024 /*align*/ + 256;
+// (operand ring depth, output staging depth): the pair must fit 227 KB of shared memory
+constexpr int smem_bytes(int ctas, int stages, int out_stages) {
+  return stages * (A_STAGE_BYTES + B_STAGE_BYTES / ctas) + out_stages * OUT_STAGE_BYTES + 1024 /*align*/ + 256;
+}
+
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -101,6 +112,35 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared::cluster address of the same shared-memory offset in the pair's leader CTA (rank 0)
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(0u));
+  return r;
+}
+// Executed by both CTAs of a pair: the bytes land in the local shared memory, the transaction count
+// on the LEADER's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_addr(bar)),
+         "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
@@ -116,25 +156,52 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CTAS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CTAS == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CTAS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+  if (CTAS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
+template <int CTAS>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n"
-      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  if (CTAS == 1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
+// Arrives on `bar` (same offset in every CTA of the pair for CTAS=2) when the MMAs issued so far retire.
+template <int CTAS>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (CTAS == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -188,30 +255,36 @@ struct GemmParams {
   const __nv_bfloat16* addend;  // DGRAD: out += addend[M, ldadd] (second contribution to a shared input)
   int64_t ldadd;
   int use_tma_store;
+  int debug;                  // MNRF_GEMM_DEBUG (timing experiments only): 1 = skip the epilogue, 2 = skip stores
   float* colsum;              // DGRAD: colsum[N] += column sums of the output (bias gradient of the
                               // layer that produced the masking activation), from the epilogue registers
   void* out;
 };
 
-template <int MODE>
+template <int MODE, int CTAS, int NUM_STAGES, int OUT_STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  constexpr int B_STAGE = B_STAGE_BYTES / CTAS;    // each CTA of a pair stages half of the B tile
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NUM_STAGES * A_STAGE_BYTES;
-  uint8_t* smem_out = smem + NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + NUM_OUT_STAGES * OUT_STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [NUM_STAGES]
+  uint8_t* smem_out = smem + NUM_STAGES * (A_STAGE_BYTES + B_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + OUT_STAGES * OUT_STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [NUM_STAGES]  (CTAS=2: the leader's are used)
   uint64_t* empty_bar = bars + NUM_STAGES;         // [NUM_STAGES]
   uint64_t* tfull_bar = bars + 2 * NUM_STAGES;     // [NUM_ACC]
-  uint64_t* tempty_bar = tfull_bar + NUM_ACC;      // [NUM_ACC]
+  uint64_t* tempty_bar = tfull_bar + NUM_ACC;      // [NUM_ACC]     (CTAS=2: the leader's are used)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + NUM_ACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
+  const int rank = CTAS == 1 ? 0 : (int)cluster_ctarank();     // CTA within its pair; 0 = leader
+  const int worker = blockIdx.x / CTAS;                        // tile owner (CTA or CTA pair)
+  const int num_workers = gridDim.x / CTAS;
+  const int num_m_units = p.num_m_blocks / CTAS;               // 128*CTAS-row units
+  const int total_tiles = num_m_units * p.num_n_blocks * p.num_splits;
   constexpr bool kWgrad = (MODE == MNRF_GEMM_WGRAD);
 
   if (warp == 0 && elect_one()) {
@@ -221,56 +294,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < NUM_ACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NUM_EPI_WARPS * 32); }
+    for (int i = 0; i < NUM_ACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTAS * NUM_EPI_WARPS * 32); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  if (warp == 2) tmem_alloc<CTAS>(tmem_ptr, 512);
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 1) __syncthreads(); else cluster_sync_all();    // peers must see initialised barriers
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+  const int b_rows = p.block_n / CTAS;             // B-tile rows this CTA stages
+  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)b_rows * BLOCK_K * 2;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
         const int n_blk = tile % p.num_n_blocks;
         const int rest = tile / p.num_n_blocks;
-        const int m_blk = rest % p.num_m_blocks;
-        const int split = rest / p.num_m_blocks;
+        const int m_blk = (rest % num_m_units) * CTAS + rank;
+        const int split = rest / num_m_units;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kblocks_per_split);
+        const int b_row0 = n_blk * p.block_n + rank * b_rows;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_bytes * CTAS);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-          uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * B_STAGE;
           if (!kWgrad) {
             // K-major: box = [64 k][rows]
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n);
+            if (CTAS == 1) {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, b_row0);
+            } else {
+              tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+              tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, b_row0);
+            }
           } else {
             // MN-major: one box per 64-wide MN atom = [64 mn][64 r], atoms BLOCK_K*128 bytes apart
-            for (int a = 0; a < BLOCK_M / 64; ++a)
-              tma_load_2d(sa + a * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + a * 64, kb * BLOCK_K);
-            for (int a = 0; a < p.block_n / 64; ++a)
-              tma_load_2d(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_blk * p.block_n + a * 64, kb * BLOCK_K);
+            for (int a = 0; a < BLOCK_M / 64; ++a) {
+              if (CTAS == 1) tma_load_2d(sa + a * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + a * 64, kb * BLOCK_K);
+              else tma_load_2d_pair(sa + a * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + a * 64, kb * BLOCK_K);
+            }
+            for (int a = 0; a < b_rows / 64; ++a) {
+              if (CTAS == 1) tma_load_2d(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], b_row0 + a * 64, kb * BLOCK_K);
+              else tma_load_2d_pair(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], b_row0 + a * 64, kb * BLOCK_K);
+            }
           }
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(BLOCK_M, p.block_n, kWgrad ? 1 : 0, kWgrad ? 1 : 0);
+    // ===================== MMA issuer (CTAS=2: leader CTA only) =====================
+    if (rank == 0) {
+    const uint32_t idesc = make_idesc(BLOCK_M * CTAS, p.block_n, kWgrad ? 1 : 0, kWgrad ? 1 : 0);
     uint32_t stage = 0, phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
       const int rest = tile / p.num_n_blocks;
-      const int split = rest / p.num_m_blocks;
+      const int split = rest / num_m_units;
       const int kb0 = split * p.kblocks_per_split;
       const int kb1 = min(p.num_k_blocks, kb0 + p.kblocks_per_split);
       const int acc = it & 1;
@@ -283,7 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             uint64_t adesc, bdesc;
@@ -297,14 +382,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               adesc = make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
               bdesc = make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
             }
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16<CTAS>(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          umma_commit<CTAS>(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
+          if (kb == kb1 - 1) umma_commit<CTAS>(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
         if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       }
+    }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -313,36 +399,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // the two warps of a quadrant split the tile's columns (tiles narrower than 128: warp-half 0 only)
     const int cols_per_half = p.block_n >= 128 ? p.block_n / 2 : p.block_n;
     const int c_begin = (ew >> 2) * cols_per_half;
-    const int c_end = min(p.block_n, c_begin + cols_per_half);
+    const int ncols = max(0, min(p.block_n, c_begin + cols_per_half) - c_begin);   // <= 128
+    const int w_begin = c_begin >> 5;       // first 32-column mask word of this warp's columns
+    const int nwords = (ncols + 31) >> 5;   // <= 4
+    // Column sums stay in registers across this CTA's tiles when their n_blk repeats with period 1
+    // or 2 (a worker's tiles are num_workers apart): one atomic per column per CTA instead of per tile.
+    const int cs_step = num_workers % p.num_n_blocks;
+    const int cs_period = cs_step == 0 ? 1 : (2 * cs_step == p.num_n_blocks ? 2 : 0);
+    const bool cs_resident = cs_period != 0;
+    float csacc[4] = {0.f, 0.f, 0.f, 0.f};     // tiles 0, 2, 4, ... of this CTA (all tiles for period 1)
+    float csodd[4] = {0.f, 0.f, 0.f, 0.f};     // tiles 1, 3, 5, ... (period 2)
+    int cs_ncol0 = -1, cs_ncol1 = -1;
+    uint32_t store_it = 0;
+
+    // per-row inputs of a tile (DGRAD): fetched one tile ahead so their latency hides behind the
+    // previous tile's epilogue
+    float rv_next = 0.f;
+    uint32_t mb_next[4] = {0u, 0u, 0u, 0u};
+    auto fetch_row_inputs = [&](int tile) {
+      rv_next = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mb_next[w] = 0u;
+      if (MODE != MNRF_GEMM_DGRAD || tile >= total_tiles) return;
+      const int n_blk = tile % p.num_n_blocks;
+      const int m_blk = ((tile / p.num_n_blocks) % num_m_units) * CTAS + rank;
+      const int64_t row = (int64_t)m_blk * BLOCK_M + q * 32 + lane;
+      if (row >= p.m) return;
+      if (p.rowv) rv_next = p.rowv[row];
+      if (p.maskbits && ncols > 0) {
+        const int64_t mrow = p.mask_mod > 0 ? row % p.mask_mod : row;
+        const uint32_t* mp = p.maskbits + mrow * p.ldmaskbits + ((n_blk * p.block_n) >> 5) + w_begin;
+        if (nwords == 4) {
+          const uint4 t = *reinterpret_cast<const uint4*>(mp);
+          mb_next[0] = t.x; mb_next[1] = t.y; mb_next[2] = t.z; mb_next[3] = t.w;
+        } else {
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (w < nwords) mb_next[w] = mp[w];
+        }
+      }
+    };
+    fetch_row_inputs(worker);
+
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
       const int n_blk = tile % p.num_n_blocks;
       const int rest = tile / p.num_n_blocks;
-      const int m_blk = rest % p.num_m_blocks;
+      const int m_blk = (rest % num_m_units) * CTAS + rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t row = (int64_t)m_blk * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.m;
       const int ncol0 = n_blk * p.block_n;
-      // per-row inputs are fetched before waiting for the accumulator
-      float rv = 0.f;
-      uint32_t mbits[MAX_BLOCK_N / 32];
+      const float rv = rv_next;
+      uint32_t mbits[4];
 #pragma unroll
-      for (int w = 0; w < MAX_BLOCK_N / 32; ++w) mbits[w] = 0u;
-      if (MODE == MNRF_GEMM_DGRAD) {
-        if (p.rowv && row_ok) rv = p.rowv[row];
-        if (p.maskbits && row_ok) {
-          const int64_t mrow = p.mask_mod > 0 ? row % p.mask_mod : row;
-          const uint32_t* mp = p.maskbits + mrow * p.ldmaskbits + (ncol0 >> 5);
-#pragma unroll
-          for (int w = 0; w < MAX_BLOCK_N / 32; ++w)
-            if (w * 32 < p.block_n) mbits[w] = mp[w];
-        }
-      }
+      for (int w = 0; w < 4; ++w) mbits[w] = mb_next[w];
+      fetch_row_inputs(tile + num_workers);
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N;
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      if (!(p.debug & 1)) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci * 32 >= ncols) break;
+        const int c0 = c_begin + ci * 32;
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);
         const int col = ncol0 + c0;
@@ -388,7 +509,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               v[j] = fmaxf(v[j], 0.f);
               bits |= (v[j] > 0.f ? 1u : 0u) << j;
             }
-            mbits[c0 >> 5] = bits;
+            mbits[ci] = bits;
           }
         } else {
           if (p.rowv) {
@@ -404,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           if (p.maskbits) {
-            const uint32_t bits = mbits[c0 >> 5];
+            const uint32_t bits = mbits[ci];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (bits >> j) & 1u ? v[j] : 0.f;
           } else if (p.mask && row_ok) {
@@ -452,7 +573,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               t[i] = keep + __shfl_xor_sync(0xffffffffu, send, sh);
             }
           }
-          atomicAdd(p.colsum + col + lane, t[0]);
+          if (!cs_resident) atomicAdd(p.colsum + col + lane, t[0]);
+          else if (cs_period == 2 && (it & 1)) csodd[ci] += t[0];
+          else csacc[ci] += t[0];
         }
         uint4 o[4];
 #pragma unroll
@@ -462,13 +585,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           o[g].z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
           o[g].w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
         }
+        if (p.debug & 2) continue;
         if (p.use_tma_store) {
           // 64-column groups: two 32-column halves share one 32x128-byte swizzled staging slab
-          const int half = (c0 >> 5) & 1;
-          uint8_t* slab = smem_out + ew * (32 * 128);
+          const int half = ci & 1;
+          uint8_t* slab = smem_out + (ew * OUT_STAGES + (store_it % OUT_STAGES)) * (32 * 128);
           if (half == 0) {
             // the bulk store previously issued from this slab must have finished reading it
-            if (lane == 0) tma_store_wait_read<0>();
+            if (lane == 0) tma_store_wait_read<OUT_STAGES - 1>();
             __syncwarp();
           }
 #pragma unroll
@@ -483,6 +607,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_store_2d(&tmap_c, slab, ncol0 + c0 - 32, m_blk * BLOCK_M + q * 32);
               tma_store_commit();
             }
+            ++store_it;
           }
         } else if (row_ok) {
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col);
@@ -491,26 +616,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (c0 + g * 8 < p.block_n) dst[g] = o[g];
         }
       }
+      }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      if (MODE == MNRF_GEMM_FWD && p.act == MNRF_ACT_RELU && p.maskbits && row_ok) {
-        uint32_t* mp = p.maskbits + row * p.ldmaskbits + (ncol0 >> 5);
-        if (p.block_n == MAX_BLOCK_N) {
-          if (ew < 4) reinterpret_cast<uint4*>(mp)[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-          else reinterpret_cast<uint4*>(mp)[1] = make_uint4(mbits[4], mbits[5], mbits[6], mbits[7]);
+      if (CTAS == 1) mbar_arrive(&tempty_bar[acc]); else mbar_arrive_leader(&tempty_bar[acc]);
+      if (cs_period == 2 && (it & 1)) cs_ncol1 = ncol0; else cs_ncol0 = ncol0;
+      if (MODE == MNRF_GEMM_FWD && p.act == MNRF_ACT_RELU && p.maskbits && row_ok && ncols > 0) {
+        uint32_t* mp = p.maskbits + row * p.ldmaskbits + (ncol0 >> 5) + w_begin;
+        if (nwords == 4) {
+          *reinterpret_cast<uint4*>(mp) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
         } else {
 #pragma unroll
-          for (int w = 0; w < MAX_BLOCK_N / 32; ++w)
-            if (w * 32 >= c_begin && w * 32 < c_end) mp[w] = mbits[w];
+          for (int w = 0; w < 4; ++w)
+            if (w < nwords) mp[w] = mbits[w];
         }
+      }
+    }
+    if (MODE == MNRF_GEMM_DGRAD && p.colsum && cs_resident) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci * 32 + 32 > ncols) continue;
+        if (cs_ncol0 >= 0) atomicAdd(p.colsum + cs_ncol0 + c_begin + ci * 32 + lane, csacc[ci]);
+        if (cs_ncol1 >= 0) atomicAdd(p.colsum + cs_ncol1 + c_begin + ci * 32 + lane, csodd[ci]);
       }
     }
     if (p.use_tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (CTAS == 1) __syncthreads(); else cluster_sync_all();    // no peer may still signal this CTA's barriers
+  if (warp == 2) tmem_dealloc<CTAS>(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -594,11 +728,18 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   if (bias) MNRF_CHECK(((uintptr_t)bias % 16) == 0, "mnrf_gemm(tc): bias must be 16-byte aligned");
   if (colv) MNRF_CHECK(((uintptr_t)colv % 16) == 0, "mnrf_gemm(tc): colv must be 16-byte aligned");
   p.use_tma_store = (d->mode != MNRF_GEMM_WGRAD && p.block_n % 64 == 0) ? 1 : 0;
+  static const int cfg_ctas = getenv("MNRF_GEMM_CTAS") ? atoi(getenv("MNRF_GEMM_CTAS")) : 2;
+  static const int cfg_stages = getenv("MNRF_GEMM_STAGES") ? atoi(getenv("MNRF_GEMM_STAGES")) : 0;
+  static const int cfg_debug = getenv("MNRF_GEMM_DEBUG") ? atoi(getenv("MNRF_GEMM_DEBUG")) : 0;
+  p.debug = cfg_debug;
   const int sms = mnrf_num_sms();
+  // CTA pairs (tcgen05 cta_group::2) whenever the tile grid is made of whole 256 x 256 tiles
+  const int ctas = (cfg_ctas == 2 && p.block_n == MAX_BLOCK_N && d->m % (2 * BLOCK_M) == 0 && sms % 2 == 0) ? 2 : 1;
+  const int workers = sms / ctas;
   p.num_splits = 1;
   if (d->mode == MNRF_GEMM_WGRAD) {
-    const int out_tiles = p.num_m_blocks * p.num_n_blocks;
-    int splits = std::max(1, (2 * sms) / out_tiles);
+    const int out_tiles = (p.num_m_blocks / ctas) * p.num_n_blocks;
+    int splits = std::max(1, (2 * workers) / out_tiles);
     splits = std::min(splits, p.num_k_blocks);
     p.num_splits = splits;
   }
@@ -615,24 +756,43 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   memset(&tc, 0, sizeof(tc));
   if (d->mode != MNRF_GEMM_WGRAD) {
     if (make_tmap(&ta, a, d->m, d->k, d->lda, BLOCK_K, BLOCK_M)) return 1;
-    if (make_tmap(&tb, b, d->n, d->k, d->ldb, BLOCK_K, p.block_n)) return 1;
+    if (make_tmap(&tb, b, d->n, d->k, d->ldb, BLOCK_K, p.block_n / ctas)) return 1;
     if (p.use_tma_store && make_tmap(&tc, out, d->m, d->n, d->ldc, 64, 32)) return 1;
   } else {
     // A = X[R, Mo], B = dY[R, N]; reduction index on rows
     if (make_tmap(&ta, a, d->k, d->m, d->lda, 64, BLOCK_K)) return 1;
     if (make_tmap(&tb, b, d->k, d->n, d->ldb, 64, BLOCK_K)) return 1;
   }
-  const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
-  const int grid = std::min(total_tiles, sms);
+  const int total_tiles = (p.num_m_blocks / ctas) * p.num_n_blocks * p.num_splits;
+  const int grid = std::min(total_tiles, workers) * ctas;
   if (grid == 0) return 0;
-#define MNRF_LAUNCH_TC(MODE_)                                                                         \
+#define MNRF_LAUNCH_TC2(MODE_, CTAS_, ST_, OST_)                                                      \
   do {                                                                                                \
     static bool attr_set = false;                                                                     \
+    constexpr int kSmem = smem_bytes(CTAS_, ST_, OST_);                                               \
+    static_assert(kSmem <= 232448, "shared memory budget");                                           \
+    auto kern = gemm_tc_kernel<MODE_, CTAS_, ST_, OST_>;                                              \
     if (!attr_set) {                                                                                  \
-      MNRF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+      MNRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));      \
       attr_set = true;                                                                                \
     }                                                                                                 \
-    gemm_tc_kernel<MODE_><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p);                      \
+    cudaLaunchConfig_t cfg = {};                                                                      \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS);                                       \
+    cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;                                                \
+    cudaLaunchAttribute attr[1];                                                                      \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                 \
+    attr[0].val.clusterDim.x = CTAS_; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;     \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                               \
+    MNRF_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));                                         \
+  } while (0)
+#define MNRF_LAUNCH_TC(MODE_)                                                                         \
+  do {                                                                                                \
+    if (ctas == 2) {                                                                                  \
+      if (cfg_stages == 5) MNRF_LAUNCH_TC2(MODE_, 2, 5, 2);                                           \
+      else MNRF_LAUNCH_TC2(MODE_, 2, 6, 1);                                                           \
+    } else {                                                                                          \
+      MNRF_LAUNCH_TC2(MODE_, 1, 4, 1);                                                                \
+    }                                                                                                 \
   } while (0)
   if (d->mode == MNRF_GEMM_FWD) MNRF_LAUNCH_TC(MNRF_GEMM_FWD);
   else if (d->mode == MNRF_GEMM_DGRAD) MNRF_LAUNCH_TC(MNRF_GEMM_DGRAD);

@@ -286,7 +286,9 @@ def _bf(x):
 
 @pytest.mark.parametrize('impl', [1, 0])
 @pytest.mark.parametrize('M,N,K', [(128, 256, 64), (256, 256, 512), (1000, 128, 320), (384, 1024, 1536),
-                                   (130, 64, 128), (4096, 256, 256)])
+                                   (130, 64, 128), (4096, 256, 256), (38000, 256, 64), (10000, 768, 128),
+                                   # whole 256-row units: CTA-pair (cta_group::2) variant, several tiles per pair
+                                   (38144, 256, 64), (10240, 1024, 256), (512, 512, 128)])
 def test_gemm_fwd(ops, impl, M, N, K):
   from multinerf_b200 import lib as L
   rng = np.random.default_rng(M + N + K)
@@ -311,7 +313,12 @@ def test_gemm_fwd(ops, impl, M, N, K):
 
 
 @pytest.mark.parametrize('impl', [1, 0])
-@pytest.mark.parametrize('M,N,K', [(256, 256, 256), (1000, 1024, 1024), (384, 256, 128)])
+@pytest.mark.parametrize('M,N,K', [(256, 256, 256), (1000, 1024, 1024), (384, 256, 128),
+                                   # several tiles per persistent CTA: row inputs prefetched a tile ahead,
+                                   # column sums resident in registers (N=768: 3 column blocks, not resident)
+                                   (38000, 256, 256), (10000, 1024, 256), (10000, 768, 128),
+                                   # CTA-pair variant (M % 256 == 0)
+                                   (37888, 256, 256), (10240, 1024, 256), (10240, 768, 128)])
 def test_gemm_dgrad(ops, impl, M, N, K):
   from multinerf_b200 import lib as L
   rng = np.random.default_rng(M + 7 * N + K)
@@ -345,7 +352,7 @@ def test_gemm_dgrad(ops, impl, M, N, K):
 
 @pytest.mark.parametrize('impl', [1, 0])
 @pytest.mark.parametrize('R,Mo,N', [(64, 128, 256), (4096, 512, 256), (8192, 320, 128), (2048, 1536, 1024),
-                                    (1024, 64, 64)])
+                                    (1024, 64, 64), (65536, 256, 256)])
 def test_gemm_wgrad(ops, impl, R, Mo, N):
   from multinerf_b200 import lib as L
   rng = np.random.default_rng(R + Mo + N)
