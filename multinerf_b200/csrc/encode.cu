@@ -203,6 +203,110 @@ encode_kernel(mnrf_encode_desc d, const float* __restrict__ sdist,
   }
 }
 
+// Fast path (no tangent rows): work items are (sample, basis direction) pairs, G samples at a time so
+// that G*K items fill whole 32-lane passes (K = 21: G = 3 -> 63 of 64 slots).  A lane lifts its own
+// (mean, variance) onto its basis direction and walks the L degrees by exact doubling
+// (y *= 2, var *= 4 give bit-identical values to lm * 2^l, lv * 4^l), so the inner loop carries no
+// shared-memory exchange, no warp sync and no index arithmetic.  Rows are staged in shared memory
+// and leave as 16-byte stores.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+encode_fast_kernel(mnrf_encode_desc d, int G, const float* __restrict__ sdist,
+                   const float* __restrict__ origins, const float* __restrict__ directions,
+                   const float* __restrict__ radii, const float* __restrict__ near,
+                   const float* __restrict__ far, const float* __restrict__ basis,
+                   __nv_bfloat16* __restrict__ feat, float* __restrict__ feat_f32,
+                   float* __restrict__ tdist_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int S = d.num_samples, K = d.basis_k, L = d.max_deg - d.min_deg, KL = K * L;
+  float* sb = reinterpret_cast<float*>(smem_raw);                 // basis [K][3]
+  const int row_bytes = ((d.feat_cols * 2 + 15) / 16) * 16;
+  const int row_elems = row_bytes / 2;
+  const int per_warp_f = (S + 1) + S * kGaussStride;
+  float* tds = sb + 3 * K + (size_t)wib * per_warp_f;
+  float* gs = tds + (S + 1);
+  unsigned char* rows = smem_raw + (((size_t)(3 * K + nw * per_warp_f) * 4 + 15) / 16) * 16;
+  __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(rows + (size_t)wib * G * row_bytes);
+
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) sb[i] = basis[i];
+  __syncthreads();
+  for (int i = lane; i < G * row_elems; i += 32) row[i] = __float2bfloat16(0.f);   // zero pad columns once
+  const float sc0 = __int_as_float((127 + d.min_deg) << 23);       // 2^min_deg
+  const int chunks = row_bytes / 16;
+
+  for (int ray = blockIdx.x * nw + wib; ray < d.num_rays; ray += gridDim.x * nw) {
+    const float o[3] = {origins[ray * 3 + 0], origins[ray * 3 + 1], origins[ray * 3 + 2]};
+    const float dv[3] = {directions[ray * 3 + 0], directions[ray * 3 + 1], directions[ray * 3 + 2]};
+    const float radius = radii[ray];
+    const float s_near = fwd_raydist(d.raydist_fn, near[ray]);
+    const float s_far = fwd_raydist(d.raydist_fn, far[ray]);
+    __syncwarp();
+    for (int i = lane; i <= S; i += 32) {
+      float t = s_to_t(d.raydist_fn, sdist[(size_t)ray * (S + 1) + i], s_near, s_far);
+      tds[i] = t;
+      if (tdist_out) tdist_out[(size_t)ray * (S + 1) + i] = t;
+    }
+    __syncwarp();
+    // phase A: one lane per sample -- Gaussian of the frustum, contracted
+    for (int s = lane; s < S; s += 32) {
+      Gauss g;
+      cast_one(d.ray_shape, tds[s], tds[s + 1], o, dv, radius, g);
+      if (d.warp_contract) contract_gauss(g);
+      float* gp = gs + s * kGaussStride;
+      gp[0] = g.mean[0]; gp[1] = g.mean[1]; gp[2] = g.mean[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gp[3 + i * 3 + j] = g.cov[i][j];
+    }
+    __syncwarp();
+    // phase B: G samples at a time
+    for (int s0 = 0; s0 < S; s0 += G) {
+      const int g = min(G, S - s0);
+      for (int j = lane; j < g * K; j += 32) {
+        const int sl = j / K;
+        const int k = j - sl * K;
+        const float* gp = gs + (s0 + sl) * kGaussStride;
+        const float b0 = sb[k * 3 + 0], b1 = sb[k * 3 + 1], b2 = sb[k * 3 + 2];
+        const float lm = gp[0] * b0 + gp[1] * b1 + gp[2] * b2;
+        const float c0 = gp[3] * b0 + gp[4] * b1 + gp[5] * b2;
+        const float c1 = gp[6] * b0 + gp[7] * b1 + gp[8] * b2;
+        const float c2 = gp[9] * b0 + gp[10] * b1 + gp[11] * b2;
+        const float lv = d.disable_integration ? 0.f : (b0 * c0 + b1 * c1 + b2 * c2);
+        float y = lm * sc0;
+        float v = lv * (sc0 * sc0);
+        __nv_bfloat16* rp = row + sl * row_elems + k;
+        float* fp = feat_f32 ? feat_f32 + ((size_t)ray * S + s0 + sl) * (size_t)(2 * KL) + k : nullptr;
+#pragma unroll 4
+        for (int l = 0; l < L; ++l) {
+          // exp(-v/2): (-0.5 v) is exact, so one multiply by -0.5*log2(e) rounds like __expf's own
+          const float e = ex2_ftz(v * -0.72134751081466674805f);
+          const float fs = e * safe_sin_fast(y);
+          const float fc = e * safe_sin_fast(y + 1.57079637050628662109375f);
+          rp[l * K] = __float2bfloat16(fs);
+          rp[KL + l * K] = __float2bfloat16(fc);
+          if (fp) { fp[l * K] = fs; fp[KL + l * K] = fc; }
+          y = y * 2.f;
+          v = v * 4.f;
+        }
+      }
+      __syncwarp();
+      for (int r = 0; r < g; ++r) {
+        const uint4* src = reinterpret_cast<const uint4*>(row + r * row_elems);
+        uint4* dst = reinterpret_cast<uint4*>(feat + ((size_t)ray * S + s0 + r) * (size_t)d.ld_feat);
+        for (int c = lane; c < chunks; c += 32) dst[c] = src[c];
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void viewdir_enc_kernel(int num_rays, int S, int deg, const float* __restrict__ viewdirs,
                                    __nv_bfloat16* __restrict__ out, int ld, int col0, int col_end) {
   // one thread per (row, column) of the [col0, col_end) slab; consecutive threads -> columns
@@ -253,14 +357,33 @@ static int encode_impl(const mnrf_encode_desc* d, const float* sdist, const floa
   if (d->num_rays == 0) return 0;
   int nw = 8;
   const int row_bytes = ((d->feat_cols * 2 + 15) / 16) * 16;
+  int blocks = ceil_div(d->num_rays, nw);
+  const int max_blocks = mnrf_num_sms() * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (!tfeat) {
+    // samples per group: fill the 32-lane passes over (sample, direction) items as fully as possible
+    int G = 1;
+    double best = 0.0;
+    for (int g = 1; g <= 16 && g <= d->num_samples; ++g) {
+      const int items = g * d->basis_k;
+      const double eff = (double)items / (32.0 * ((items + 31) / 32));
+      if (eff > best + 1e-9) { best = eff; G = g; }
+    }
+    size_t smem = (((size_t)(3 * d->basis_k + nw * ((d->num_samples + 1) + d->num_samples * kGaussStride)) * 4 + 15) / 16) * 16 +
+                  (size_t)nw * G * row_bytes;
+    MNRF_CHECK(smem <= 200 * 1024, "mnrf_encode: shared memory %zu too large", smem);
+    MNRF_CUDA(cudaFuncSetAttribute(encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    encode_fast_kernel<<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
+        *d, G, sdist, origins, directions, radii, near, far, basis,
+        reinterpret_cast<__nv_bfloat16*>(feat_bf16), feat_f32, tdist_out);
+    MNRF_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = (((size_t)(3 * d->basis_k + nw * ((d->num_samples + 1) + d->num_samples * kGaussStride +
                                                    2 * d->basis_k)) * 4 + 15) / 16) * 16 +
                 (size_t)nw * row_bytes * (tfeat ? 4 : 1);
   MNRF_CHECK(smem <= 200 * 1024, "mnrf_encode: shared memory %zu too large", smem);
   MNRF_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int blocks = ceil_div(d->num_rays, nw);
-  const int max_blocks = mnrf_num_sms() * 8;
-  if (blocks > max_blocks) blocks = max_blocks;
   encode_kernel<<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
       *d, sdist, origins, directions, radii, near, far, basis,
       reinterpret_cast<__nv_bfloat16*>(feat_bf16), feat_f32, tdist_out,
