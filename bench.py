@@ -207,6 +207,13 @@ def run_ours(args):
   peak_tf, peak_hbm, peak_kind = peaks()
   canon_flops_step = TRAIN_FLOP_PER_RAY * B          # per rank
   achieved = canon_flops_step / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+  # DRAM bytes per GEMM launch from the committed ncu --set full capture (tools/summarize_profile.py)
+  traffic = None
+  tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'gemm_tc_traffic.json')
+  if os.path.exists(tpath) and B == 16384:
+    with open(tpath) as f:
+      traffic = json.load(f).get('dram_bytes_per_launch')
+  n_gemm = max(1, len(evs))
   out = {
       'metric': 'train-step rays/sec @16384 rays x (64+64+32) samples',
       'value': rays_per_s, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -222,7 +229,10 @@ def run_ours(args):
               'ms_per_step': ms_e2e / args.steps},
       'gpu_launches': int(launches),
       'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                   'frac': achieved / peak_tf if peak_tf else None, 'traffic': None,
+                   'frac': achieved / peak_tf if peak_tf else None, 'traffic': traffic,
+                   'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
+                   'launches_per_step': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm,
+                   'algorithmic_flop_per_launch': canon_flops_step / n_gemm,
                    'kernel': 'gemm_tc_kernel (tcgen05 fwd+dgrad+wgrad)', 'peak_kind': peak_kind + ' sustained bf16',
                    'gemm_ms_per_step': gemm_ms, 'gemm_share_of_step': gemm_ms / (ms / args.steps),
                    'executed_tflops': gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0,

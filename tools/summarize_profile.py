@@ -66,3 +66,15 @@ if rep:
       for i in idx:
         f.write(f'{hdr[i]} [{units[i]}] = {row[i][:100]}\n')
   print('wrote ncu summary')
+  # per-launch DRAM traffic of the dominant kernel -> bench.py's roofline.traffic
+  if 'gemm_tc' in os.path.basename(rep):
+    import json
+    ir, iw, it = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot = [float(row[ir].replace(',', '')) * scale[units[ir]] + float(row[iw].replace(',', '')) * scale[units[iw]]
+           for row in r[2:]]
+    with open(os.path.join(out_dir, 'gemm_tc_traffic.json'), 'w') as f:
+      json.dump({'kernel': 'gemm_tc_kernel', 'launches': len(tot), 'dram_bytes_per_launch': sum(tot) / len(tot),
+                 'source': f'profiles/{tag}_gemm_tc_ncu.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, '
+                           'every GEMM launch of one 360.gin train step)'}, f, indent=1)
+    print('wrote gemm_tc_traffic.json', sum(tot) / len(tot) / 1e9, 'GB per launch')
