@@ -276,6 +276,36 @@ int mnrf_outer_mask(int64_t rows, int32_t n, int64_t mask_mod, const float* rowv
                     const uint32_t* maskbits, int64_t ldmaskbits, mnrf_bf16* out, int64_t ldo,
                     mnrf_stream stream);
 
+/* ---- ray generation (the step before the path) --------------------------
+ * camera_utils.pixels_to_rays (camera_utils.py:522-636) + the camera gather of
+ * camera_utils.cast_ray_batch (:639-688), as the reference runs it on the device when
+ * Config.cast_rays_in_train_step is set (train_utils.py:266-268): half-pixel offset, inverse
+ * intrinsics, optional radial/tangential undistortion (_radial_and_tangential_undistort
+ * :478-513, Newton steps), optional fisheye model, OpenCV->OpenGL flip, camera rotation,
+ * optional NDC projection (convert_to_ndc :32-97), mip-NeRF cone radii from the dx/dy neighbours.
+ * pixtocams [num_cameras, 3, 3] and camtoworlds [num_cameras, 3, 4] are row-major fp32;
+ * cam_idx may be NULL when num_cameras == 1.  Outputs are [num_rays, 3|3|3|1|2] fp32.
+ */
+#define MNRF_CAM_PERSPECTIVE 0
+#define MNRF_CAM_FISHEYE 1
+typedef struct {
+  int32_t num_rays;
+  int32_t num_cameras;
+  int32_t camtype;
+  int32_t has_distortion;
+  float k1, k2, k3, k4, p1, p2;
+  float undistort_eps;        /* 1e-9 in the reference */
+  int32_t undistort_iters;    /* 10 in the reference */
+  int32_t has_ndc;
+  float ndc_p02, ndc_p12;     /* pixtocam_ndc[0][2], pixtocam_ndc[1][2] */
+  float ndc_near;             /* 1.0 in the reference */
+} mnrf_camera_desc;
+
+int mnrf_pixels_to_rays(const mnrf_camera_desc* d, const int32_t* pix_x, const int32_t* pix_y,
+                        const int32_t* cam_idx, const float* pixtocams, const float* camtoworlds,
+                        float* origins, float* directions, float* viewdirs, float* radii,
+                        float* imageplane, mnrf_stream stream);
+
 /* ---- optimizer ---------------------------------------------------------------------------
  * train_utils.clip_gradients (train_utils.py:200-218: value clip, then global-norm clip with
  * eps in the denominator), nan_to_num (:328) and optax.adam on one flat fp32 parameter

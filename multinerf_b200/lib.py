@@ -62,6 +62,14 @@ class RefdirDesc(C.Structure):
               ('col_end', C.c_int32)]
 
 
+class CameraDesc(C.Structure):
+  _fields_ = [('num_rays', C.c_int32), ('num_cameras', C.c_int32), ('camtype', C.c_int32),
+              ('has_distortion', C.c_int32), ('k1', C.c_float), ('k2', C.c_float), ('k3', C.c_float),
+              ('k4', C.c_float), ('p1', C.c_float), ('p2', C.c_float), ('undistort_eps', C.c_float),
+              ('undistort_iters', C.c_int32), ('has_ndc', C.c_int32), ('ndc_p02', C.c_float),
+              ('ndc_p12', C.c_float), ('ndc_near', C.c_float)]
+
+
 class AdamDesc(C.Structure):
   _fields_ = [('n', C.c_int64), ('grad_max_val', C.c_float), ('grad_max_norm', C.c_float),
               ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
@@ -99,6 +107,7 @@ _SIGNATURES = {
     'mnrf_refdir_bwd': (C.c_int, [C.POINTER(RefdirDesc)] + [_P] * 8 + [C.c_int32, C.c_float, C.c_float, C.c_int32] +
                         [_P] * 8),
     'mnrf_outer_mask': (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, _P]),
+    'mnrf_pixels_to_rays': (C.c_int, [C.POINTER(CameraDesc)] + [_P] * 11),
     'mnrf_clip_adam': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 6),
     'mnrf_clip_adam_dyn': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 7),
     'mnrf_pack_weights': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P]),

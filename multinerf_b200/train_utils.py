@@ -16,6 +16,7 @@ import math
 import torch
 import torch.distributed as dist
 
+from . import camera_utils
 from . import configs
 from . import models
 from . import ops
@@ -62,8 +63,12 @@ def _anneal(mcfg, train_frac):
   return 1.0
 
 
-def create_train_step(model: models.Model, config: configs.Config, impl=0, use_graph=False):
+def create_train_step(model: models.Model, config: configs.Config, impl=0, use_graph=False, dataset=None):
   """Returns train_pstep (train_utils.py:221-346) for this rank's shard of the batch.
+
+  With `config.cast_rays_in_train_step`, `batch.rays` is a utils.Pixels and the rays are generated
+  on the device from `cameras` first (train_utils.py:266-268; camera type from `dataset.camtype`
+  as train_utils.py:234-237).
 
   use_graph=True captures the step into two CUDA graphs (forward+backward | clip+Adam+repack,
   with the NCCL all-reduce between them) after one eager warm-up step; per-step scalars
@@ -71,6 +76,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
   buffers that are refreshed before each replay, so train_frac and the step count may advance.
   """
   mcfg = model.mcfg
+  camtype = getattr(dataset, 'camtype', camera_utils.ProjectionType.PERSPECTIVE)
   if config.data_loss_type not in ('mse', 'charb', 'rawnerf'):
     raise NotImplementedError(f'data_loss_type {config.data_loss_type!r}')
   if use_graph and (mcfg.near_anneal_rate is not None or
@@ -202,7 +208,15 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     if model.params is not params:
       model.bind(params)
       G['state'] = 0
-    rays = batch.rays if hasattr(batch.rays, 'radii_flat') else model._prep_rays(batch.rays)
+    rays = batch.rays
+    if config.cast_rays_in_train_step:
+      if not isinstance(rays, utils.Pixels):
+        raise ValueError('cast_rays_in_train_step: batch.rays must be a utils.Pixels')
+      if cameras is None:
+        raise ValueError('cast_rays_in_train_step: cameras = (pixtocams, camtoworlds, distortion_params, '
+                         'pixtocam_ndc) is required')
+      rays = camera_utils.cast_ray_batch(cameras, rays, camtype, device=dev)
+    rays = rays if hasattr(rays, 'radii_flat') else model._prep_rays(rays)
     B = rays.origins.shape[0]
     target = torch.as_tensor(batch.rgb).to(dev, torch.float32).reshape(B, -1)[:, :3].contiguous()
     sched = model.level_schedule(train_frac)[2]
@@ -342,5 +356,5 @@ def setup_model(config, rng, dataset=None, device=None):
   model, variables = models.construct_model(rng, dummy, bundle, device=device)
   state, lr_fn = create_optimizer(bundle.config, variables)
   render_eval_pfn = create_render_fn(model)
-  train_pstep = create_train_step(model, bundle.config)
+  train_pstep = create_train_step(model, bundle.config, dataset=dataset)
   return model, state, render_eval_pfn, train_pstep, lr_fn

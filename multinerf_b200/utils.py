@@ -12,6 +12,19 @@ import torch
 
 
 @dataclasses.dataclass
+class Pixels:
+  """internal/utils.py:31-41: integer pixel coordinates [SH] + per-ray metadata [SH, 1]."""
+  pix_x_int: Any
+  pix_y_int: Any
+  lossmult: Any
+  near: Any
+  far: Any
+  cam_idx: Any
+  exposure_idx: Optional[Any] = None
+  exposure_values: Optional[Any] = None
+
+
+@dataclasses.dataclass
 class Rays:
   origins: Any
   directions: Any

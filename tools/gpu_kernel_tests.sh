@@ -8,5 +8,6 @@ run() { echo "=== $*" ; timeout 900 python -m pytest -m gpu -q -p no:cacheprovid
 run tests/test_gpu_kernels.py -k "not gemm"
 run tests/test_gpu_kernels.py -k "gemm"
 TAILN=120 run tests/test_gpu_model.py
+run tests/test_gpu_camera.py
 } > gpurun_out/kernel_tests.log 2>&1
 tail -250 gpurun_out/kernel_tests.log
