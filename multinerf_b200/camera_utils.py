@@ -40,9 +40,16 @@ def _dev(x, dtype, device):
   return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
 
 
+_checked = False
+
+
 def _launch(pix_x, pix_y, cam_idx, pixtocams, camtoworlds, distortion_params, pixtocam_ndc, camtype):
   """All inputs flat on the device; returns the five [B, n] fp32 outputs."""
-  lib = L.require_device()
+  global _checked
+  if not _checked:
+    L.require_device()          # queries device properties: once, not per launch
+    _checked = True
+  lib = L.load()
   B = pix_x.shape[0]
   dev = pix_x.device
   if isinstance(camtype, str):

@@ -66,15 +66,37 @@ if rep:
       for i in idx:
         f.write(f'{hdr[i]} [{units[i]}] = {row[i][:100]}\n')
   print('wrote ncu summary')
-  # per-launch DRAM traffic of the dominant kernel -> bench.py's roofline.traffic
-  if 'gemm_tc' in os.path.basename(rep):
-    import json
-    ir, iw, it = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
-    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-    tot = [float(row[ir].replace(',', '')) * scale[units[ir]] + float(row[iw].replace(',', '')) * scale[units[iw]]
-           for row in r[2:]]
-    with open(os.path.join(out_dir, 'gemm_tc_traffic.json'), 'w') as f:
-      json.dump({'kernel': 'gemm_tc_kernel', 'launches': len(tot), 'dram_bytes_per_launch': sum(tot) / len(tot),
-                 'source': f'profiles/{tag}_gemm_tc_ncu.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, '
-                           'every GEMM launch of one 360.gin train step)'}, f, indent=1)
-    print('wrote gemm_tc_traffic.json', sum(tot) / len(tot) / 1e9, 'GB per launch')
+
+# per-launch DRAM traffic of the dominant kernel over one whole step (light metric set, every GEMM
+# launch) -> profiles/<tag>_gemm_traffic.txt and bench.py's roofline.traffic
+tp = os.path.join(ROOT, 'gpurun_out', 'gemm_traffic.csv')
+if os.path.exists(tp):
+  import json
+  lines = [l for l in open(tp) if l.startswith('"')]
+  per = collections.OrderedDict()
+  for r in csv.DictReader(lines):
+    d = per.setdefault(int(r['ID']), {'kernel': re.sub(r'\(.*', '', r['Kernel Name']).replace('void ', '')})
+    v = float(r['Metric Value'].replace(',', ''))
+    unit = r['Metric Unit']
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'nsecond': 1.0, 'usecond': 1e3, 'msecond': 1e6,
+             'second': 1e9}.get(unit, 1.0)
+    d[r['Metric Name']] = v * scale
+  rows = list(per.values())
+  tot = [r['dram__bytes_read.sum'] + r['dram__bytes_write.sum'] for r in rows]
+  with open(os.path.join(out_dir, f'{tag}_gemm_traffic.txt'), 'w') as f:
+    f.write('# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,'
+            'sm__pipe_tensor_cycles_active...,lts__t_bytes.sum --clock-control none\n')
+    f.write(f'# every gemm_tc_kernel launch of one 360.gin train step (16384 rays): {len(rows)} launches, '
+            f'DRAM {sum(tot) / 1e9:.2f} GB per step, {sum(tot) / len(tot) / 1e9:.4f} GB per launch on average\n')
+    f.write('#  i  kernel<mode,ctas,stages,out>            time_us  dram_rd_MB  dram_wr_MB  L2_GB  tensor_pipe_%\n')
+    for i, r in enumerate(rows):
+      f.write(f"{i:4d}  {r['kernel'][:38]:38s} {r['gpu__time_duration.sum'] / 1e3:9.1f} "
+              f"{r['dram__bytes_read.sum'] / 1e6:10.1f} {r['dram__bytes_write.sum'] / 1e6:10.1f} "
+              f"{r.get('lts__t_bytes.sum', 0) / 1e9:7.2f} "
+              f"{r.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0):8.1f}\n")
+  with open(os.path.join(out_dir, 'gemm_tc_traffic.json'), 'w') as f:
+    json.dump({'kernel': 'gemm_tc_kernel', 'launches': len(tot), 'dram_bytes_per_launch': sum(tot) / len(tot),
+               'dram_bytes_per_step': sum(tot),
+               'source': f'profiles/{tag}_gemm_traffic.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum, '
+                         'every GEMM launch of one 360.gin train step)'}, f, indent=1)
+  print('wrote gemm_tc_traffic.json:', sum(tot) / len(tot) / 1e9, 'GB per launch,', sum(tot) / 1e9, 'GB per step')
