@@ -315,11 +315,11 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  base = cpu_baseline(args.cpu_rays, max(1, args.steps), max(0, min(args.warmup, 1)))
+  base = cpu_baseline(args.cpu_rays, max(1, args.steps), max(0, min(args.warmup, 3)))
   out = {
       'impl': 'reference', 'metric': 'train-step rays/sec @16384 rays x (64+64+32) samples',
       'value': base['value'], 'unit': 'rays/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
-      'steps': max(1, args.steps), 'warmup': max(0, min(args.warmup, 1)),
+      'steps': max(1, args.steps), 'warmup': max(0, min(args.warmup, 3)),
       'ms_per_step': base['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': args.scaling,
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': 'mip-NeRF 360 (360.gin) train step, bounded sample of %d rays per step on the '
@@ -343,8 +343,10 @@ def main():
   ap.add_argument('--no_graph', action='store_true', help='launch every kernel from Python (no CUDA graphs)')
   args = ap.parse_args()
   if args.impl == 'reference':
-    if args.steps > 3:
-      args.steps = 3          # each CPU step is a bounded sample; keep the run to a few minutes
+    # exactly K timed steps; each step is a bounded ray sample of the workload, shrunk for large K so
+    # that the whole run stays within about a minute of CPU time (256 rays ~ 0.8 s per step)
+    if args.steps > 60:
+      args.cpu_rays = max(32, int(args.cpu_rays * 60 / args.steps) // 32 * 32)
     run_reference(args)
     return
   world = int(os.environ.get('WORLD_SIZE', '1'))
