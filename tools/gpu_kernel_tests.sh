@@ -9,5 +9,6 @@ run tests/test_gpu_kernels.py -k "not gemm"
 run tests/test_gpu_kernels.py -k "gemm"
 TAILN=120 run tests/test_gpu_model.py
 run tests/test_gpu_camera.py
+run tests/test_gpu_train_loop.py
 } > gpurun_out/kernel_tests.log 2>&1
 tail -250 gpurun_out/kernel_tests.log
