@@ -11,6 +11,8 @@ OBJ = os.path.join(HERE, '..', 'build', 'obj')
 LIB = os.path.join(HERE, 'libmnrf_b200.so')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+if os.environ.get('MNRF_TIMING_KNOBS') == '1':      # tools/gemm_variants.sh: main-loop-only timing of the GEMM
+  COMMON.append('-DMNRF_TIMING_KNOBS')
 # The per-ray geometry/compositing kernels are compiled without FMA contraction so that their
 # fp32 rounding follows the reference's unfused elementwise graph (tight oracle parity); the
 # GEMM and reduction kernels keep FMA.

@@ -730,7 +730,12 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   p.use_tma_store = (d->mode != MNRF_GEMM_WGRAD && p.block_n % 64 == 0) ? 1 : 0;
   static const int cfg_ctas = getenv("MNRF_GEMM_CTAS") ? atoi(getenv("MNRF_GEMM_CTAS")) : 2;
   static const int cfg_stages = getenv("MNRF_GEMM_STAGES") ? atoi(getenv("MNRF_GEMM_STAGES")) : 0;
+#ifdef MNRF_TIMING_KNOBS
+  // timing experiments only (results are wrong by construction): compiled in only on request
   static const int cfg_debug = getenv("MNRF_GEMM_DEBUG") ? atoi(getenv("MNRF_GEMM_DEBUG")) : 0;
+#else
+  static const int cfg_debug = 0;
+#endif
   p.debug = cfg_debug;
   const int sms = mnrf_num_sms();
   // CTA pairs (tcgen05 cta_group::2) whenever the tile grid is made of whole 256 x 256 tiles

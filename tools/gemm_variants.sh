@@ -6,5 +6,5 @@ echo "=== default (CTA pairs: 6 operand stages, 1 output stage)"; timeout 300 py
 if [ -n "$ALL_VARIANTS" ]; then
 echo "=== MNRF_GEMM_STAGES=5 (CTA pairs: 5 operand stages, 2 output stages)"; MNRF_GEMM_STAGES=5 timeout 300 python tools/gemm_bench.py
 echo "=== MNRF_GEMM_CTAS=1 (single CTA: 4 operand stages, 1 output stage)"; MNRF_GEMM_CTAS=1 timeout 300 python tools/gemm_bench.py
-echo "=== MNRF_GEMM_DEBUG=1 (CTA pairs, no epilogue: main-loop ceiling)"; MNRF_GEMM_DEBUG=1 timeout 300 python tools/gemm_bench.py
+echo "=== MNRF_GEMM_DEBUG=1 (needs a library built with MNRF_TIMING_KNOBS=1; CTA pairs, no epilogue: main-loop ceiling)"; MNRF_GEMM_DEBUG=1 timeout 300 python tools/gemm_bench.py
 fi
