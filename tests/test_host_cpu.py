@@ -216,3 +216,31 @@ def test_world_size_2_collectives_gloo():
     assert rgb == [0.0] * 4 + [1.0] * 4                   # rank r's rows at [r*n, (r+1)*n)
     assert acc == [0., 1., 2., 3., 10., 11., 12., 13.]
     assert rs == float(rank)                              # ray_* bundles stay local
+
+
+def test_checkpoint_roundtrip_cpu(tmp_path):
+  """checkpoints.save/restore/latest on host tensors (state = step + params + Adam moments; layout
+  mismatch is an error; `keep` prunes the oldest files) -- train.py:84,219-223 semantics."""
+  import torch
+  from multinerf_b200 import checkpoints, configs, models, train_utils
+  b = configs.bundle_360()
+  plans = {'NerfMLP_0': models.MLPPlan(b.nerf_mlp, True), 'PropMLP_0': models.MLPPlan(b.prop_mlp, True)}
+  p = models.Params(plans, 'cpu', {})
+  g = torch.Generator().manual_seed(0)
+  for buf in (p.flat, p.mu, p.nu):
+    buf.copy_(torch.randn(buf.shape, generator=g))
+  p.step = 7
+  state = train_utils.TrainState(p)
+  d = str(tmp_path / 'ck')
+  assert checkpoints.latest_checkpoint(d) is None
+  assert checkpoints.restore_checkpoint(d, state) is state and state.step == 7      # nothing to restore
+  for s in (1, 5, 7):
+    checkpoints.save_checkpoint(d, state, s, keep=2)
+  assert sorted(os.listdir(d)) == ['checkpoint_5', 'checkpoint_7']
+  assert checkpoints.latest_checkpoint(d).endswith('checkpoint_7')
+  q = models.Params(plans, 'cpu', {})
+  st2 = checkpoints.restore_checkpoint(d, train_utils.TrainState(q))
+  assert st2.step == 7 and torch.equal(q.flat, p.flat) and torch.equal(q.mu, p.mu) and torch.equal(q.nu, p.nu)
+  other = models.Params({'NerfMLP_0': plans['NerfMLP_0']}, 'cpu', {})
+  with pytest.raises(ValueError):
+    checkpoints.restore_checkpoint(d, train_utils.TrainState(other))
