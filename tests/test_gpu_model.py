@@ -456,3 +456,68 @@ def test_glo_embeddings_vs_oracle(mods):
   b = grads_o[('Embed_0', 'embedding')].double().flatten()
   rel = float((a - b).norm() / b.norm())
   assert float(b.norm()) > 0 and rel < 0.15, rel
+
+
+def test_full_size_properties(mods):
+  """BASELINE size (360.gin: 16384 rays x (64+64+32) samples, PropMLP 4x256, NerfMLP 8x1024), where the
+  oracle is too slow: size-independent properties of the path.
+    * every level: sdist sorted inside [0,1], weights >= 0 with sum <= 1, colours inside the padded
+      sigmoid range, percentiles ordered, everything finite;
+    * rays are independent: rendering the batch == rendering its two halves, bit for bit;
+    * the loss is a mean over rays: grad(batch) == (grad(half 1) + grad(half 2)) / 2 up to bf16 noise."""
+  models, train_utils = mods
+  from multinerf_b200 import configs, utils
+  bundle = configs.bundle_360()
+  B = 16384
+  rays, rng = synth_rays(21, B, 0.2, 1e6)
+  model, variables = models.construct_model(3, rays, bundle)
+  assert model.num_params() == 9007493
+  rend, hist = model(None, rays, 1.0, True)
+  torch.cuda.synchronize()
+  S = [64, 64, 32]
+  pad = bundle.nerf_mlp.rgb_padding
+  for lvl, (r, h) in enumerate(zip(rend, hist)):
+    sd, w = h['sdist'], h['weights']
+    assert sd.shape == (B, S[lvl] + 1) and w.shape == (B, S[lvl])
+    assert bool((sd[:, 1:] >= sd[:, :-1]).all()) and float(sd.min()) >= 0.0 and float(sd.max()) <= 1.0
+    assert float(w.min()) >= 0.0 and float(w.sum(-1).max()) <= 1.0 + 1e-5
+    assert bool(torch.isfinite(r['rgb']).all()) and float(r['rgb'].min()) >= -pad - 1e-6 and float(r['rgb'].max()) <= 1 + pad + 1e-6
+    assert float(r['acc'].min()) >= 0.0 and float(r['acc'].max()) <= 1.0 + 1e-5
+    assert bool((r['distance_percentile_5'] <= r['distance_median'] + 1e-6).all())
+    assert bool((r['distance_median'] <= r['distance_percentile_95'] + 1e-6).all())
+    assert bool(torch.isfinite(r['distance_mean']).all()) and bool(torch.isfinite(h['density']).all())
+  full_rgb = rend[-1]['rgb'].clone()
+  full_w = hist[-1]['weights'].clone()
+  import dataclasses
+  halves = []
+  for sl in (slice(0, B // 2), slice(B // 2, B)):
+    sub = utils.Rays(**{f.name: (None if getattr(rays, f.name) is None else getattr(rays, f.name)[sl])
+                        for f in dataclasses.fields(rays)})
+    r2, h2 = model(None, sub, 1.0, True)
+    halves.append((r2[-1]['rgb'].clone(), h2[-1]['weights'].clone(), sub))
+  assert torch.equal(torch.cat([halves[0][0], halves[1][0]]), full_rgb)
+  assert torch.equal(torch.cat([halves[0][1], halves[1][1]]), full_w)
+
+  # gradient of the mean loss = mean of the halves' gradients (same parameters, no optimizer step applied)
+  target = rng.uniform(0, 1, (B, 3)).astype(np.float32)
+  cfg = copy.deepcopy(bundle.config)
+  cfg.lr_init = cfg.lr_final = 1e-30            # keep the parameters (and their bf16 copies) fixed
+  jit = [torch.tensor(rng.uniform(0, 1, (B, 1)).astype(np.float32)) for _ in range(3)]
+  step_fn = train_utils.create_train_step(model, cfg)
+  state = train_utils.TrainState(variables)
+
+  def grad_of(sl):
+    sub = utils.Rays(**{f.name: (None if getattr(rays, f.name) is None else getattr(rays, f.name)[sl])
+                        for f in dataclasses.fields(rays)})
+    nonlocal state
+    state, stats, _ = step_fn({'jitter': [j[sl] for j in jit]}, state, utils.Batch(rays=sub, rgb=target[sl]), None, 0.5)
+    torch.cuda.synchronize()
+    return model.params.grads.clone().double(), stats.materialize()['loss']
+
+  g_full, l_full = grad_of(slice(0, B))
+  g1, l1 = grad_of(slice(0, B // 2))
+  g2, l2 = grad_of(slice(B // 2, B))
+  g_sum = 0.5 * (g1 + g2)
+  rel = float((g_full - g_sum).norm() / g_full.norm())
+  assert rel < 2e-2, rel
+  assert abs(l_full - 0.5 * (l1 + l2)) < 1e-4 * abs(l_full), (l_full, l1, l2)
