@@ -128,6 +128,7 @@ extern "C" int mnrf_pixels_to_rays(const mnrf_camera_desc* d, const int32_t* pix
                                    float* imageplane, mnrf_stream stream) {
   using namespace mnrf;
   set_error("");
+  if (d && d->num_rays == 0) return 0;            // nothing to do (and empty tensors carry null pointers)
   MNRF_CHECK(d && pix_x && pix_y && pixtocams && camtoworlds && origins && directions && viewdirs && radii &&
              imageplane, "mnrf_pixels_to_rays: null pointer");
   MNRF_CHECK(d->num_cameras >= 1, "mnrf_pixels_to_rays: num_cameras must be >= 1");

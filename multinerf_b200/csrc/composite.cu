@@ -475,6 +475,7 @@ extern "C" int mnrf_composite_fwd(const mnrf_composite_desc* d, const float* raw
                                   float* weights, float* rgb_out, float* density_out,
                                   float* rgb_samples, float* acc, float* dist, mnrf_stream stream) {
   using namespace mnrf;
+  if (d && d->num_rays == 0) return 0;
   MNRF_CHECK(d && raw_density && sdist && directions && near && far && weights && rgb_out,
              "mnrf_composite_fwd: null pointer");
   MNRF_CHECK(d->num_samples >= 1 && d->num_samples <= 256, "mnrf_composite_fwd: num_samples %d > 256",
@@ -507,6 +508,7 @@ extern "C" int mnrf_composite_bwd(const mnrf_loss_desc* d, const float* raw_dens
   using namespace mnrf;
   MNRF_CHECK(d->c.rgb_mode == 0 || (raw_rgb && raw_diffuse && d_raw_diffuse && (!raw_tint || d_raw_tint)),
              "mnrf_composite_bwd: rgb_mode 1 needs raw_diffuse / d_raw_diffuse (and d_raw_tint with raw_tint)");
+  if (d && d->c.num_rays == 0) return 0;
   MNRF_CHECK(d && raw_density && sdist && directions && near && far && target_rgb && lossmult &&
              inv_denom && d_raw_density && stats, "mnrf_composite_bwd: null pointer");
   MNRF_CHECK(d->c.num_samples >= 1 && d->c.num_samples <= 256, "mnrf_composite_bwd: num_samples %d > 256",

@@ -340,6 +340,7 @@ static int encode_impl(const mnrf_encode_desc* d, const float* sdist, const floa
                        float* feat_f32, float* tdist_out, mnrf_bf16* tfeat, int ld_tfeat,
                        mnrf_stream stream) {
   using namespace mnrf;
+  if (d && d->num_rays == 0) return 0;            // nothing to do (and empty tensors carry null pointers)
   if (tfeat) {
     MNRF_CHECK(!d->warp_contract, "mnrf_encode_tangent: density normals with a contraction warp are not supported");
     MNRF_CHECK(ld_tfeat >= d->feat_cols && ld_tfeat % 8 == 0 && ((uintptr_t)tfeat % 16) == 0,
@@ -405,6 +406,7 @@ extern "C" int mnrf_encode_tangent(const mnrf_encode_desc* d, const float* sdist
                                    const float* far, const float* basis, mnrf_bf16* feat_bf16,
                                    mnrf_bf16* tfeat_bf16, int32_t ld_tfeat, mnrf_stream stream) {
   mnrf::set_error("");
+  if (d && d->num_rays == 0) return 0;
   if (!tfeat_bf16) { mnrf::set_error("mnrf_encode_tangent: null tangent buffer"); return 1; }
   return encode_impl(d, sdist, origins, directions, radii, near, far, basis, feat_bf16, nullptr, nullptr,
                      tfeat_bf16, ld_tfeat, stream);
@@ -414,6 +416,7 @@ extern "C" int mnrf_viewdir_enc(int32_t num_rays, int32_t num_samples, int32_t d
                                 const float* viewdirs, mnrf_bf16* out, int32_t ld, int32_t col0,
                                 int32_t col_end, mnrf_stream stream) {
   using namespace mnrf;
+  if (num_rays == 0) return 0;
   MNRF_CHECK(viewdirs && out, "mnrf_viewdir_enc: null pointer");
   MNRF_CHECK(col_end - col0 >= 3 + 6 * deg && col_end <= ld, "mnrf_viewdir_enc: slab [%d,%d) too small for deg %d",
              col0, col_end, deg);

@@ -80,6 +80,7 @@ extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf
                          const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
                          float* colsum, const mnrf_bf16* addend, void* out, mnrf_stream stream) {
   using namespace mnrf;
+  if (d && (d->m == 0 || d->n == 0 || d->k == 0)) return 0;   // empty operand: nothing to compute or accumulate
   MNRF_CHECK(d && a && b && out, "mnrf_gemm: null pointer");
   MNRF_CHECK(d->mode >= 0 && d->mode <= 2, "mnrf_gemm: unknown mode %d", d->mode);
   MNRF_CHECK((rowv == nullptr) == (colv == nullptr), "mnrf_gemm: rowv and colv come together");

@@ -692,7 +692,10 @@ static int pick_block_n(int n) {
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                    const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
                    float* colsum, const mnrf_bf16* addend, void* out, cudaStream_t stream) {
-  MNRF_CHECK(d->k % BLOCK_K == 0, "mnrf_gemm(tc): reduction length %d must be a multiple of %d", d->k, BLOCK_K);
+  // K-major modes: the reduction index is the contiguous one and layers are padded to 64.  WGRAD reduces
+  // over the sample rows, any count: the last 64-row block is zero-filled by TMA past the tensor's end.
+  MNRF_CHECK(d->mode == MNRF_GEMM_WGRAD || d->k % BLOCK_K == 0,
+             "mnrf_gemm(tc): reduction length %d must be a multiple of %d", d->k, BLOCK_K);
   MNRF_CHECK(d->lda % 8 == 0 && d->ldb % 8 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0,
              "mnrf_gemm(tc): operands must be 16-byte aligned with ld %% 8 == 0");
   GemmParams p{};
@@ -703,7 +706,7 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
     MNRF_CHECK(p.block_n >= 64, "mnrf_gemm(tc): WGRAD needs N %% 64 == 0 (MN-major 128-byte atoms), N=%d", d->n);
   p.num_m_blocks = (int)((d->m + BLOCK_M - 1) / BLOCK_M);
   p.num_n_blocks = d->n / p.block_n;
-  p.num_k_blocks = d->k / BLOCK_K;
+  p.num_k_blocks = (d->k + BLOCK_K - 1) / BLOCK_K;
   p.ldc = d->ldc; p.ldmask = d->ldmask;
   p.bias = bias; p.rowv = rowv; p.colv = colv;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask);

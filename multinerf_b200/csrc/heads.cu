@@ -274,6 +274,7 @@ clip_adam_kernel(mnrf_adam_desc d, float* __restrict__ p, const float* __restric
 extern "C" int mnrf_head_fwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf16* x, int64_t ldx,
                              const mnrf_bf16* w, const float* b, float* raw, mnrf_stream stream) {
   using namespace mnrf;
+  if (m == 0) return 0;
   MNRF_CHECK(x && w && raw, "mnrf_head_fwd: null pointer");
   MNRF_CHECK(n_out >= 1 && n_out <= kMaxHead, "mnrf_head_fwd: n_out %d not in [1,4]", n_out);
   MNRF_CHECK(k % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0,
@@ -292,6 +293,7 @@ extern "C" int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf1
                              const mnrf_bf16* w, const float* draw, mnrf_bf16* dx, int64_t lddx,
                              int32_t relu_mask, float* dw, float* db, float* dxsum, mnrf_stream stream) {
   using namespace mnrf;
+  if (m == 0) return 0;
   MNRF_CHECK(x && w && draw, "mnrf_head_bwd: null pointer");
   MNRF_CHECK(!dxsum || dx, "mnrf_head_bwd: dxsum needs dx");
   MNRF_CHECK(n_out >= 1 && n_out <= kMaxHead, "mnrf_head_bwd: n_out %d not in [1,4]", n_out);
@@ -327,6 +329,7 @@ extern "C" int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf1
 extern "C" int mnrf_colsum(int64_t m, int32_t n, const mnrf_bf16* x, int64_t ldx, float* out,
                            mnrf_stream stream) {
   using namespace mnrf;
+  if (m == 0) return 0;
   MNRF_CHECK(x && out, "mnrf_colsum: null pointer");
   MNRF_CHECK(n % 8 == 0 && ldx % 8 == 0, "mnrf_colsum: N and ld must be multiples of 8");
   if (m == 0) return 0;

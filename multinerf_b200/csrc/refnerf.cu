@@ -320,6 +320,7 @@ extern "C" int mnrf_refdir_fwd(const mnrf_refdir_desc* d, const float* ide_mat, 
                                mnrf_bf16* slab, float orient_mult, float prednorm_mult, int32_t orient_on_pred,
                                float* extra_dw, mnrf_stream stream) {
   using namespace mnrf;
+  if (d && d->M == 0) return 0;
   MNRF_CHECK(d && viewdirs && slab, "mnrf_refdir_fwd: null pointer");
   MNRF_CHECK(!d->use_ide || (ide_mat && ide_ml && d->ide_n <= kIdeMax && d->deg_view >= 1 && d->deg_view <= 5),
              "Only deg_view of at most 5 is numerically stable.");
@@ -346,6 +347,7 @@ extern "C" int mnrf_refdir_bwd(const mnrf_refdir_desc* d, const float* ide_mat, 
                                float* d_grad_pred, float* d_raw_rough, float* d_raw_grad_density,
                                float* stats, mnrf_stream stream) {
   using namespace mnrf;
+  if (d && d->M == 0) return 0;
   MNRF_CHECK(d && viewdirs && weights && d_slab && stats, "mnrf_refdir_bwd: null pointer");
   MNRF_CHECK(d->col_end - d->col0 >= 11, "mnrf_refdir_bwd: the slab must hold the 11 head gradients");
   MNRF_CHECK(!d->use_ide || (ide_mat && ide_ml && d->ide_n <= kIdeMax), "mnrf_refdir_bwd: bad IDE tables");
@@ -366,6 +368,7 @@ extern "C" int mnrf_outer_mask(int64_t rows, int32_t n, int64_t mask_mod, const 
                                const uint32_t* maskbits, int64_t ldmaskbits, mnrf_bf16* out, int64_t ldo,
                                mnrf_stream stream) {
   using namespace mnrf;
+  if (rows == 0) return 0;
   MNRF_CHECK(rowv && colv && out, "mnrf_outer_mask: null pointer");
   MNRF_CHECK(n % 32 == 0 && ldo % 8 == 0, "mnrf_outer_mask: N %% 32 == 0 and ld %% 8 == 0 required");
   if (rows == 0) return 0;

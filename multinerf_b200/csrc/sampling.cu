@@ -210,6 +210,7 @@ static int sample_level_impl(const mnrf_sample_desc* d, const float* sdist_prev,
                              float* cw_out, float* tdil_out, float* wdil_out,
                              const float* anneal_dev, mnrf_stream stream) {
   using namespace mnrf;
+  if (d && d->num_rays == 0) return 0;
   MNRF_CHECK(d && sdist_prev && w_prev && u_base && sdist_out, "mnrf_sample_level: null pointer");
   MNRF_CHECK(d->num_samples > 1, "num_samples must be > 1, is %d.", d->num_samples);
   MNRF_CHECK(d->num_prev >= 1 && d->num_prev <= 1024, "mnrf_sample_level: num_prev %d out of range",

@@ -352,7 +352,9 @@ def test_gemm_dgrad(ops, impl, M, N, K):
 
 @pytest.mark.parametrize('impl', [1, 0])
 @pytest.mark.parametrize('R,Mo,N', [(64, 128, 256), (4096, 512, 256), (8192, 320, 128), (2048, 1536, 1024),
-                                    (1024, 64, 64), (65536, 256, 256)])
+                                    (1024, 64, 64), (65536, 256, 256),
+                                    # sample counts that are not a multiple of the 64-row reduction block
+                                    (2080, 128, 256), (1000, 256, 256), (37, 64, 64)])
 def test_gemm_wgrad(ops, impl, R, Mo, N):
   from multinerf_b200 import lib as L
   rng = np.random.default_rng(R + Mo + N)
