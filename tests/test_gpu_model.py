@@ -561,3 +561,88 @@ def test_empty_batch(mods):
                         for f in dataclasses.fields(rays)})
   rend, hist = model(None, empty, 1.0, True)
   assert rend[-1]['rgb'].shape == (0, 3) and hist[-1]['sdist'].shape == (0, bundle.model.num_nerf_samples + 1)
+
+
+def _variant(name):
+  b = mini360()
+  m = b.model
+  if name == 'samples_128_128_64':
+    m.num_prop_samples, m.num_nerf_samples = 128, 64
+  elif name == 'four_levels':
+    m.num_levels = 4
+  elif name == 'per_sample_jitter':
+    m.single_jitter = False
+  elif name == 'cylinder':
+    m.ray_shape = 'cylinder'
+  elif name == 'no_integration':
+    # plain PE: without the Gaussian attenuation a random-init MLP of 2^11-frequency features is not a
+    # smooth function of the sample positions, so the end-to-end comparison is only well conditioned at
+    # low degrees
+    m.disable_integration = True
+    b.prop_mlp.max_deg_point = b.nerf_mlp.max_deg_point = 5
+  elif name == 'no_dilation_padded':
+    m.dilation_multiplier, m.dilation_bias, m.resample_padding = 0.0, 0.0, 0.01
+  elif name == 'gpu_resampling_flag':
+    m.use_gpu_resampling = True
+  elif name == 'piecewise_raydist':
+    m.raydist_fn = 'piecewise'
+  elif name == 'translucent_white_bg':
+    m.opaque_background, m.bg_intensity_range = False, (1.0, 1.0)
+  elif name == 'coarse_data_loss_mse':
+    b.config.data_coarse_loss_mult, b.config.data_loss_type = 0.1, 'mse'
+  else:
+    raise KeyError(name)
+  return b
+
+
+@pytest.mark.parametrize('name', ['samples_128_128_64', 'four_levels', 'per_sample_jitter', 'cylinder',
+                                  'no_integration', 'no_dilation_padded', 'gpu_resampling_flag',
+                                  'piecewise_raydist', 'translucent_white_bg', 'coarse_data_loss_mse'])
+def test_config_variants_vs_oracle(mods, name):
+  """Model / Config switches away from the shipped 360.gin values, each against the oracle: rendered
+  pixels and level-0 sample positions of a randomized forward pass, then loss, per-level MSEs and the
+  direction of every layer's gradient for one train step."""
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  bundle = _variant(name)
+  bundle.config.grad_max_norm = 0.0
+  B = 96
+  near, far = (0.5, 30.0) if name == 'piecewise_raydist' else (0.2, 1e6)
+  rays, rng = synth_rays(31, B, near, far)
+  target = rng.uniform(0, 1, (B, 3)).astype(np.float32)
+  model, variables = models.construct_model(6, rays, bundle)
+  params0 = torch_tree(model.export_flax())
+  bases = {'nerf': model.plans['NerfMLP_0'].basis, 'prop': model.plans['PropMLP_0'].basis}
+  sched = model.level_schedule(0.5)[2]
+  width = lambda lv: 1 if bundle.model.single_jitter else lv['S']
+  rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, width(lv))).astype(np.float32)) for lv in sched]}
+  with torch.no_grad():
+    rend_o, hist_o = o_models.model_apply(params0, bundle, bases, oracle_rays(rays), 0.5, True, rand=rand, bf16=True)
+  rend, hist = model(rand, rays, 0.5, True)
+  torch.cuda.synchronize()
+  assert len(rend) == bundle.model.num_levels
+  close(hist[0]['sdist'], hist_o[0]['sdist'], atol=1e-6, rtol=1e-6, msg='level-0 sdist')
+  close(rend[-1]['rgb'], rend_o[-1]['rgb'], atol=2e-2, rtol=0, msg='final pixel')
+  close(rend[-1]['acc'], rend_o[-1]['acc'], atol=2e-2, rtol=0, msg='final acc')
+  opt0 = {'count': 0, 'mu': {}, 'nu': {}}
+  _, _, stats_o, grads_o = o_train.train_step(params0, opt0, bundle, bases, oracle_rays(rays), torch.tensor(target),
+                                              0.5, rand=rand, bf16=True)
+  step_fn = train_utils.create_train_step(model, bundle.config)
+  state = train_utils.TrainState(variables)
+  state, stats, _ = step_fn(rand, state, utils.Batch(rays=rays, rgb=target), None, 0.5)
+  torch.cuda.synchronize()
+  stats.materialize()
+  close(stats['mses'], stats_o['mses'].detach(), atol=2e-3, rtol=3e-2, msg='mses')
+  lo = float(stats_o['loss'].detach())
+  assert abs(stats['loss'] - lo) < 3e-2 * max(1.0, abs(lo)), (stats['loss'], lo)
+  g = model.export_grads_flax()
+  for mname in g:
+    for lname in g[mname]:
+      a = torch.tensor(g[mname][lname]['kernel']).double().flatten()
+      b = grads_o[(mname, lname, 'kernel')].double().flatten()
+      if float(b.norm()) == 0.0:
+        assert float(a.norm()) == 0.0, (mname, lname)
+        continue
+      cos = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+      rel = float((a - b).norm() / b.norm())
+      assert cos > 0.98 and rel < 0.25, (name, mname, lname, cos, rel)
