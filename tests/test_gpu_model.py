@@ -590,6 +590,28 @@ def _variant(name):
     m.opaque_background, m.bg_intensity_range = False, (1.0, 1.0)
   elif name == 'coarse_data_loss_mse':
     b.config.data_coarse_loss_mult, b.config.data_loss_type = 0.1, 'mse'
+  # ---- MLP switches
+  elif name == 'trunk_skip_every_2':            # several skip concatenations in both trunks
+    b.nerf_mlp.skip_layer, b.prop_mlp.skip_layer, b.prop_mlp.net_depth = 2, 2, 4
+  elif name == 'deep_view_mlp':                 # view MLP with its own skip (models.py:575-580)
+    b.nerf_mlp.net_depth_viewdirs, b.nerf_mlp.skip_layer_dir = 4, 2
+  elif name == 'degrees_2_to_9_view_deg_2':
+    for c in (b.nerf_mlp, b.prop_mlp):
+      c.min_deg_point, c.max_deg_point = 2, 9
+    b.nerf_mlp.deg_view = 2
+  elif name == 'octahedron_basis':
+    for c in (b.nerf_mlp, b.prop_mlp):
+      c.basis_shape, c.basis_subdivisions = 'octahedron', 1
+  elif name == 'icosahedron_1_basis':
+    for c in (b.nerf_mlp, b.prop_mlp):
+      c.basis_subdivisions = 1
+  elif name == 'rgb_head_settings':
+    b.nerf_mlp.rgb_premultiplier, b.nerf_mlp.rgb_bias, b.nerf_mlp.rgb_padding = 2.0, -0.5, 0.0
+    b.nerf_mlp.density_bias, b.prop_mlp.density_bias = 0.5, 0.5
+  elif name == 'glorot_uniform_init':
+    b.nerf_mlp.weight_init = b.prop_mlp.weight_init = 'glorot_uniform'
+  elif name == 'single_mlp':
+    m.single_mlp = True
   else:
     raise KeyError(name)
   return b
@@ -597,7 +619,10 @@ def _variant(name):
 
 @pytest.mark.parametrize('name', ['samples_128_128_64', 'four_levels', 'per_sample_jitter', 'cylinder',
                                   'no_integration', 'no_dilation_padded', 'gpu_resampling_flag',
-                                  'piecewise_raydist', 'translucent_white_bg', 'coarse_data_loss_mse'])
+                                  'piecewise_raydist', 'translucent_white_bg', 'coarse_data_loss_mse',
+                                  'trunk_skip_every_2', 'deep_view_mlp', 'degrees_2_to_9_view_deg_2',
+                                  'octahedron_basis', 'icosahedron_1_basis', 'rgb_head_settings',
+                                  'glorot_uniform_init', 'single_mlp'])
 def test_config_variants_vs_oracle(mods, name):
   """Model / Config switches away from the shipped 360.gin values, each against the oracle: rendered
   pixels and level-0 sample positions of a randomized forward pass, then loss, per-level MSEs and the
@@ -612,7 +637,8 @@ def test_config_variants_vs_oracle(mods, name):
   target = rng.uniform(0, 1, (B, 3)).astype(np.float32)
   model, variables = models.construct_model(6, rays, bundle)
   params0 = torch_tree(model.export_flax())
-  bases = {'nerf': model.plans['NerfMLP_0'].basis, 'prop': model.plans['PropMLP_0'].basis}
+  bases = {'nerf': model.plans['NerfMLP_0'].basis,
+           'prop': model.plans.get('PropMLP_0', model.plans['NerfMLP_0']).basis}
   sched = model.level_schedule(0.5)[2]
   width = lambda lv: 1 if bundle.model.single_jitter else lv['S']
   rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, width(lv))).astype(np.float32)) for lv in sched]}
