@@ -113,6 +113,11 @@ class MLPPlan:
         add('roughness', x_dim, x_pad, 1, True, rm=rmx)
       if cfg.use_directional_enc and not cfg.enable_pred_roughness:
         raise NotImplementedError('IDE without a predicted roughness (kappa_inv would be None)')
+      if cfg.use_directional_enc and not cfg.use_reflections:
+        # models.py:548-554: dir_enc_fn(viewdirs [..., 3], roughness [..., S, 1]) does not broadcast in the
+        # reference either (ref_utils.py:141-148); every shipped config pairs IDE with reflections
+        raise ValueError('use_directional_enc needs use_reflections (per-sample roughness cannot attenuate '
+                         'the encoding of a per-ray view direction)')
       bw = cfg.bottleneck_width
       self.device_constraints.append(('bottleneck_width', bw))
       add('bottleneck', x_dim, x_pad, bw, False, L.ACT_NONE, rmx)
