@@ -746,3 +746,68 @@ def test_refnerf_variants_vs_oracle(mods, name):
     broken.nerf_mlp.use_directional_enc, broken.nerf_mlp.use_reflections = True, False
     with pytest.raises(ValueError):
       models.Model(broken)
+
+
+def _family(name, rng, B):
+  """(bundle, rays, per-level jitter width) of a reduced-size model family with per-step varying inputs."""
+  from multinerf_b200 import configs, utils
+  f = np.float32
+  if name == 'rawnerf':
+    bundle = configs.bundle_llff_raw()
+    bundle.model.num_prop_samples = bundle.model.num_nerf_samples = 32
+    bundle.nerf_mlp.net_width, bundle.nerf_mlp.bottleneck_width, bundle.nerf_mlp.net_width_viewdirs = 128, 64, 64
+    bundle.nerf_mlp.density_noise = 0.0           # the graph path refreshes jitter only from a generator or dict
+    o = np.concatenate([rng.uniform(-1, 1, (B, 2)), -np.ones((B, 1))], -1)
+    d = np.concatenate([rng.uniform(-.5, .5, (B, 2)), 2 * np.ones((B, 1))], -1)
+    eidx = rng.integers(0, 4, (B, 1)).astype(np.int32)
+    rays = utils.Rays(origins=o.astype(f), directions=d.astype(f),
+                      viewdirs=(d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(f),
+                      radii=rng.uniform(1e-3, 2e-3, (B, 1)).astype(f), imageplane=np.zeros((B, 2), f),
+                      lossmult=np.eye(3, dtype=f)[rng.integers(0, 3, B)], near=np.zeros((B, 1), f),
+                      far=np.ones((B, 1), f), cam_idx=np.zeros((B, 1), np.int32), exposure_idx=eidx,
+                      exposure_values=(2.0 ** -eidx).astype(f))
+    return bundle, rays, [32, 32]
+  if name == 'refnerf':
+    bundle = mini_refnerf()
+    rays, _ = synth_rays(int(rng.integers(1 << 30)), B, 2.0, 6.0, unit_cube=False)
+    return bundle, rays, [16, 16]
+  if name == 'glo':
+    bundle = mini360()
+    bundle.model.num_glo_features, bundle.model.num_glo_embeddings = 4, 16
+    rays, _ = synth_rays(int(rng.integers(1 << 30)), B, 0.2, 1e6)
+    rays.cam_idx = rng.integers(0, 16, (B, 1)).astype(np.int32)
+    return bundle, rays, [1, 1, 1]
+  raise KeyError(name)
+
+
+@pytest.mark.parametrize('family', ['rawnerf', 'refnerf', 'glo'])
+def test_cuda_graph_matches_eager_other_families(mods, family):
+  """Graph capture of the step for the other model families (exposure-offset and GLO scatter-adds, the
+  Ref-NeRF tangent chain and reflection stage): five steps with changing rays, targets, jitter,
+  train_frac and learning rate track the eager run."""
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  B, steps = 192, 5
+  rng = np.random.default_rng(77)
+  batches = []
+  for _ in range(steps):
+    bundle, rays, widths = _family(family, rng, B)
+    rand = {'jitter': [torch.tensor(rng.uniform(0, 1, (B, w)).astype(np.float32)) for w in widths]}
+    batches.append((rays, rng.uniform(0, 1, (B, 3)).astype(np.float32), rand))
+  results = []
+  for use_graph in [False, True]:
+    model, variables = models.construct_model(6, batches[0][0], bundle)
+    step_fn = train_utils.create_train_step(model, bundle.config, use_graph=use_graph)
+    state = train_utils.TrainState(variables)
+    losses = []
+    for i, (rays, tgt, rand) in enumerate(batches):
+      state, stats, _ = step_fn(rand, state, utils.Batch(rays=rays, rgb=tgt), None, i / 10.0)
+      losses.append(stats.materialize()['loss'])
+    torch.cuda.synchronize()
+    results.append((losses, variables.flat.clone()))
+    if use_graph:
+      assert step_fn.graph_info['state'] == 2, step_fn.graph_info['state']
+  (l0, p0), (l1, p1) = results
+  for a, b in zip(l0, l1):
+    assert abs(a - b) < 2e-3 * max(1.0, abs(a)), (l0, l1)
+  assert float((p0 - p1).norm() / p0.norm()) < 2e-3
