@@ -182,7 +182,8 @@ def run_ours(args):
     sampler.start()
   ms, _ = timed(args.steps, False)
   clocks = sampler.stop() if rank == 0 else {}
-  launches = ops.LAUNCHES // max(1, args.steps)
+  launches_total = ops.LAUNCHES                 # our kernels launched inside the timed region (all K steps)
+  launches = launches_total // max(1, args.steps)
   ms_e2e, loss_host = timed(args.steps, True)
 
   # dominant kernel (tcgen05 GEMM, all three modes): CUDA events around every launch of one
@@ -227,7 +228,7 @@ def run_ours(args):
       'e2e': {'value': rays_per_s_e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d_bytes * world),
               'd2h_bytes_per_step': int(loss_host.numel() * 4 * world) if loss_host is not None else 0,
               'ms_per_step': ms_e2e / args.steps},
-      'gpu_launches': int(launches),
+      'gpu_launches': int(launches_total), 'gpu_launches_per_step': int(launches),
       'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                    'frac': achieved / peak_tf if peak_tf else None, 'traffic': traffic,
                    'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
