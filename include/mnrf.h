@@ -330,6 +330,22 @@ int mnrf_clip_adam_dyn(const mnrf_adam_desc* d, float* params, const float* grad
 int mnrf_pack_weights(int32_t in_pad, int32_t out, const float* master, mnrf_bf16* w_nk,
                       mnrf_bf16* w_kn, mnrf_stream stream);
 
+/* The same for `count` layers in one launch (the optimizer epilogue of a train step).  `items` is a
+ * DEVICE array of mnrf_pack_item, ordered as the layers' 32x32 tiles are numbered: item i owns tiles
+ * [tile0, tile0 + ceil(out/32) * ceil(in_pad/32)), tile0 of item i+1 = the end of item i;
+ * total_tiles = the end of the last item. */
+typedef struct {
+  const float* master;
+  mnrf_bf16* w_nk;          /* may be NULL */
+  mnrf_bf16* w_kn;          /* may be NULL */
+  int32_t in_pad, out;
+  int32_t tile0;
+  int32_t reserved;
+} mnrf_pack_item;
+
+int mnrf_pack_weights_batched(int32_t count, const mnrf_pack_item* items, int32_t total_tiles,
+                              mnrf_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,6 +224,35 @@ __global__ void pack_weights_kernel(int in_pad, int out, const float* __restrict
   }
 }
 
+// One launch for every layer: blockIdx.x is a global tile number, the owning layer is found by a
+// binary search over the items' first tiles.
+__global__ void pack_weights_batched_kernel(int count, const mnrf_pack_item* __restrict__ items) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const mnrf_pack_item it = items[lo];
+  const int tiles_n = (it.out + 31) / 32;
+  const int t = blockIdx.x - it.tile0;
+  const int k0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
+  const int in_pad = it.in_pad, out = it.out;
+  __nv_bfloat16* w_nk = reinterpret_cast<__nv_bfloat16*>(it.w_nk);
+  __nv_bfloat16* w_kn = reinterpret_cast<__nv_bfloat16*>(it.w_kn);
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int k = k0 + r, n = n0 + threadIdx.x;
+    float v = (k < in_pad && n < out) ? it.master[(size_t)k * out + n] : 0.f;
+    tile[r][threadIdx.x] = v;
+    if (w_kn && k < in_pad && n < out) w_kn[(size_t)k * out + n] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int n = n0 + r, k = k0 + threadIdx.x;
+    if (w_nk && n < out && k < in_pad) w_nk[(size_t)n * in_pad + k] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 grad_norm_kernel(int64_t n, const float* __restrict__ g, float scale, float max_val,
                  float* __restrict__ norm_sq) {
@@ -353,6 +382,16 @@ extern "C" int mnrf_pack_weights(int32_t in_pad, int32_t out, const float* maste
   dim3 grid((out + 31) / 32, (in_pad + 31) / 32), block(32, 8);
   pack_weights_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
       in_pad, out, master, reinterpret_cast<__nv_bfloat16*>(w_nk), reinterpret_cast<__nv_bfloat16*>(w_kn));
+  MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mnrf_pack_weights_batched(int32_t count, const mnrf_pack_item* items, int32_t total_tiles,
+                                         mnrf_stream stream) {
+  using namespace mnrf;
+  if (count == 0 || total_tiles == 0) return 0;
+  MNRF_CHECK(items && count > 0 && total_tiles > 0, "mnrf_pack_weights_batched: null item table");
+  pack_weights_batched_kernel<<<total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(count, items);
   MNRF_LAUNCH_CHECK();
   return 0;
 }

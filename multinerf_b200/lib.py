@@ -70,6 +70,11 @@ class CameraDesc(C.Structure):
               ('ndc_p12', C.c_float), ('ndc_near', C.c_float)]
 
 
+class PackItem(C.Structure):
+  _fields_ = [('master', C.c_void_p), ('w_nk', C.c_void_p), ('w_kn', C.c_void_p), ('in_pad', C.c_int32),
+              ('out', C.c_int32), ('tile0', C.c_int32), ('reserved', C.c_int32)]
+
+
 class AdamDesc(C.Structure):
   _fields_ = [('n', C.c_int64), ('grad_max_val', C.c_float), ('grad_max_norm', C.c_float),
               ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
@@ -111,6 +116,7 @@ _SIGNATURES = {
     'mnrf_clip_adam': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 6),
     'mnrf_clip_adam_dyn': (C.c_int, [C.POINTER(AdamDesc)] + [_P] * 7),
     'mnrf_pack_weights': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    'mnrf_pack_weights_batched': (C.c_int, [C.c_int32, _P, C.c_int32, _P]),
 }
 EXPORTED = tuple(_SIGNATURES)
 

@@ -198,8 +198,10 @@ class MLPDevice:
   def repack(self):
     """fp32 master -> bf16 operand layouts (after init and after every optimizer step)."""
     plan = self.plan
-    for sp in plan.specs:
-      ops.pack_weights(self.W(sp), self.w_nk[sp.name], self.w_kn.get(sp.name))
+    if getattr(self, '_pack_table', None) is None:      # buffers never move: build the device table once
+      self._pack_table = ops.pack_table([(self.W(sp), self.w_nk[sp.name], self.w_kn.get(sp.name))
+                                         for sp in plan.specs], self.device)
+    ops.pack_weights_batched(self._pack_table)
     d = plan.one('density')
     self.colv_density = self.w_nk[d.name][0].float().contiguous()   # bf16-rounded, as the fwd used
     if plan.ref_stage:

@@ -259,6 +259,28 @@ def pack_weights(master, w_nk, w_kn):
                                 L.stream_ptr()))
 
 
+def pack_table(layers, device):
+  """Device table for pack_weights_batched: layers = [(master[in_pad,out], w_nk or None, w_kn or None)]."""
+  import ctypes
+  import numpy as np
+  items = (L.PackItem * len(layers))()
+  tile = 0
+  for i, (master, w_nk, w_kn) in enumerate(layers):
+    in_pad, out = master.shape
+    items[i] = L.PackItem(master.data_ptr(), w_nk.data_ptr() if w_nk is not None else None,
+                          w_kn.data_ptr() if w_kn is not None else None, in_pad, out, tile, 0)
+    tile += ((out + 31) // 32) * ((in_pad + 31) // 32)
+  raw = np.frombuffer(ctypes.string_at(ctypes.addressof(items), ctypes.sizeof(items)), dtype=np.uint8).copy()
+  return torch.from_numpy(raw).to(device), len(layers), tile
+
+
+def pack_weights_batched(table):
+  lib = L.load()
+  dev_items, count, tiles = table
+  _count()
+  L.check(lib.mnrf_pack_weights_batched(count, L.ptr(dev_items), tiles, L.stream_ptr()))
+
+
 def refdir_desc(M, S, *, use_pred_normals, use_density_normals, use_reflections, use_ide, use_n_dot_v,
                 use_roughness, deg_view, ide_n, roughness_bias, ld, col0, col_end):
   return L.RefdirDesc(M, S, int(use_pred_normals), int(use_density_normals), int(use_reflections),

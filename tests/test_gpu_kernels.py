@@ -401,6 +401,18 @@ def test_pack_weights_and_adam(ops):
   ops.pack_weights(master.cuda(), w_nk, w_kn)
   assert torch.equal(w_kn.cpu(), master.to(torch.bfloat16))
   assert torch.equal(w_nk.cpu(), master.T.contiguous().to(torch.bfloat16))
+  # all layers of a module in one launch (ragged shapes, an item without the w_kn copy)
+  shapes = [(320, 128), (64, 3), (100, 257), (512, 256), (33, 1)]
+  masters = [torch.tensor(rng.normal(size=sh).astype(np.float32)).cuda() for sh in shapes]
+  nks = [torch.full((o, i), 7.0, dtype=torch.bfloat16, device='cuda') for i, o in shapes]
+  kns = [None if j == 1 else torch.full((i, o), 7.0, dtype=torch.bfloat16, device='cuda') for j, (i, o) in enumerate(shapes)]
+  table = ops.pack_table(list(zip(masters, nks, kns)), 'cuda')
+  ops.pack_weights_batched(table)
+  torch.cuda.synchronize()
+  for mst, nk, kn in zip(masters, nks, kns):
+    assert torch.equal(nk, mst.T.contiguous().to(torch.bfloat16))
+    if kn is not None:
+      assert torch.equal(kn, mst.to(torch.bfloat16))
 
   class Cfg:
     adam_beta1, adam_beta2, adam_eps = 0.9, 0.999, 1e-6
