@@ -21,7 +21,16 @@ import tempfile
 import threading
 import time
 
-import numpy as np
+# The CPU arm must own the host's threads.  torchrun exports OMP_NUM_THREADS=1 to every rank, which
+# (set before the OpenMP / MKL runtimes start) would throttle the reference arm by two orders of
+# magnitude, so that arm resets the variables before numpy / torch are imported.
+if '--impl' in sys.argv and sys.argv[sys.argv.index('--impl') + 1:sys.argv.index('--impl') + 2] == ['reference'] \
+    or '--impl=reference' in sys.argv:
+  _t = str(min(os.cpu_count() or 1, int(os.environ.get('MNRF_CPU_THREADS', '32'))))
+  for _k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+    os.environ[_k] = _t
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
