@@ -244,3 +244,28 @@ def test_checkpoint_roundtrip_cpu(tmp_path):
   other = models.Params({'NerfMLP_0': plans['NerfMLP_0']}, 'cpu', {})
   with pytest.raises(ValueError):
     checkpoints.restore_checkpoint(d, train_utils.TrainState(other))
+
+
+def test_camera_host_helpers():
+  """multinerf_b200.camera_utils host one-liners vs the oracle's (camera_utils.py:398-424) and the
+  Pixels container (internal/utils.py:31-41)."""
+  import torch
+  from multinerf_b200 import camera_utils, utils
+  from oracle import o_camera
+  p = camera_utils.get_pixtocam(123.0, 64, 48)
+  np.testing.assert_allclose(p, o_camera.get_pixtocam(123.0, 64, 48).numpy(), atol=1e-15)
+  np.testing.assert_allclose(camera_utils.intrinsic_matrix(1.0, 2.0, 3.0, 4.0),
+                             o_camera.intrinsic_matrix(1.0, 2.0, 3.0, 4.0).numpy())
+  x, y = camera_utils.pixel_coordinates(5, 3)
+  ox, oy = o_camera.pixel_coordinates(5, 3)
+  assert x.shape == (3, 5) and np.array_equal(x, ox.numpy()) and np.array_equal(y, oy.numpy())
+  assert camera_utils.ProjectionType('fisheye') is camera_utils.ProjectionType.FISHEYE
+  px = utils.Pixels(pix_x_int=x, pix_y_int=y, lossmult=None, near=None, far=None, cam_idx=None)
+  assert px.exposure_idx is None and px.exposure_values is None
+  with pytest.raises(lib_error()):
+    camera_utils.pixels_to_rays(x, y, p, np.eye(4)[:3], device='cpu')      # no CPU path
+
+
+def lib_error():
+  from multinerf_b200 import lib
+  return (lib.MnrfError, RuntimeError, AssertionError)
