@@ -7,13 +7,13 @@ models,train_utils}.py`).  It exists to CHECK the CUDA path; nothing in
 `bench.py`'s `cpu_baseline` / `--impl reference` legs use it.
 
 Pinning status (see DESIGN.md "Oracle"):
-  * L2 functions (stepfun / render / coord / math / ref_utils / geopoly / image)
+  * L2 functions (stepfun / render / coord / math / ref_utils / geopoly / image / camera_utils)
     are pinned against (a) the reference's own known-answer tests, re-stated in
     `tests/test_oracle_*.py`, and (b) golden vectors produced by executing the
     REAL reference source files in this container under a numpy stand-in for
     `jax.numpy` (`tests/golden/make_golden.py`, fixtures in `tests/golden/*.npz`).
   * `Model.__call__` / `MLP.__call__` (all four BASELINE model families: mip-NeRF 360, blender,
-    RawNeRF, Ref-NeRF) and the loss functions / clip_gradients of the train-step closure are
+    RawNeRF, Ref-NeRF; plus GLO vectors, random backgrounds, bottleneck noise and near-plane annealing) and the loss functions / clip_gradients of the train-step closure are
     pinned the same way: `tests/golden/make_golden_model.py` runs the reference's REAL
     `internal/models.py` and `internal/train_utils.py` under jax/flax/gin stand-ins and
     `tests/test_oracle_model_golden.py` compares `oracle.o_models.model_apply` and

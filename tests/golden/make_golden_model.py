@@ -122,6 +122,16 @@ CASES = {
                      basis_shape='octahedron', basis_subdivisions=1, disable_density_normals=True,
                      max_deg_point=16, rgb_padding=0., rgb_activation=rmath.safe_exp, rgb_bias=-5.,
                      density_noise=1.)),
+    'miniglo': dict(        # GLO vectors, random backgrounds, bottleneck noise, near-plane annealing
+        near=0.2, far=1e6, rays='cube', B=20, train_frac=0.2, cam_idx=6,
+        Config=dict(),
+        Model=dict(raydist_fn=jnp.reciprocal, num_prop_samples=12, num_nerf_samples=8, num_glo_features=4,
+                   num_glo_embeddings=6, bg_intensity_range=(0.2, 0.9), near_anneal_rate=0.5,
+                   near_anneal_init=0.9),
+        PropMLP=dict(warp_fn=coord.contract, net_depth=2, net_width=32, disable_density_normals=True,
+                     disable_rgb=True),
+        NerfMLP=dict(warp_fn=coord.contract, net_depth=5, net_width=48, bottleneck_width=16,
+                     net_width_viewdirs=24, disable_density_normals=True, bottleneck_noise=0.3)),
     'minirefnerf': dict(
         near=2.0, far=6.0, rays='sphere', B=12, train_frac=0.7,
         Config=dict(data_loss_type='mse', distortion_loss_mult=0.0, orientation_loss_mult=0.1,
@@ -147,7 +157,7 @@ def _name(v):
 
 def run_case(tag, spec, save):
   rng = np.random.default_rng(abs(hash(tag)) % 2 ** 31 if False else {'mini360': 1, 'plumbing': 2, 'miniraw': 3,
-                                                                      'minirefnerf': 4}[tag])
+                                                                      'minirefnerf': 4, 'miniglo': 5}[tag])
   gin.clear()
   for cls in ['Model', 'PropMLP', 'NerfMLP']:
     gin.bind(cls, **spec[cls])
@@ -155,6 +165,9 @@ def run_case(tag, spec, save):
   model = models.Model(config=config)
   B = spec['B']
   rays = _rays(rng, B, spec['near'], spec['far'], spec['rays'], spec.get('exposure', False))
+  if spec.get('cam_idx'):
+    import dataclasses
+    rays = dataclasses.replace(rays, cam_idx=rng.integers(0, spec['cam_idx'], (B, 1)).astype(np.int32))
   params = _init_params(model, rng, rays)
   out = {'meta_tag': np.array(tag)}
   for cls in ['Config', 'Model', 'PropMLP', 'NerfMLP']:
@@ -183,6 +196,15 @@ def run_case(tag, spec, save):
           nz = rng.normal(size=(B, S)).astype(F)
           draws.append(nz)
           out[f'{mode}/density_noise{lv}'] = nz
+        if mlp_bind.get('bottleneck_noise', 0) > 0 and not mlp_bind.get('disable_rgb', False):
+          bn = rng.normal(size=(B, S, mlp_bind.get('bottleneck_width', 256))).astype(F)   # models.py:529-533
+          draws.append(bn)
+          out[f'{mode}/bottleneck_noise{lv}'] = bn
+        lo, hi = spec['Model'].get('bg_intensity_range', (1., 1.))
+        if lo != hi:
+          bg = rng.uniform(0, 1, (B, 3)).astype(F)                                         # models.py:249-254
+          draws.append(bg)
+          out[f'{mode}/bg{lv}'] = bg
       key = jax.random.Stream(draws)
     renderings, ray_history = model.apply({'params': params}, key, rays, train_frac=spec['train_frac'],
                                           compute_extras=True, zero_glo=False)
@@ -208,7 +230,7 @@ def run_case(tag, spec, save):
   class FakeGrad(dict):
     pass
   g = {'params': {k: {kk: {n: (rng.normal(size=np.asarray(a).shape) * 0.05).astype(F) for n, a in vv.items()}
-                      if isinstance(vv, dict) else None for kk, vv in v.items()} if k != 'exposure_scaling_offsets'
+                      if isinstance(vv, dict) else None for kk, vv in v.items()} if 'embedding' not in v
                   else {'embedding': (rng.normal(size=np.asarray(v['embedding']).shape) * 0.05).astype(F)}
                   for k, v in params.items()}}
   clipped = train_utils.clip_gradients(FakeGrad(g), config)

@@ -22,7 +22,10 @@ def load(tag):
     if k.startswith('bind/'):
       _, cls, attr = k.split('/')
       v = g[k]
-      v = v.item() if v.dtype.kind in 'biuf' else str(v)
+      if v.dtype.kind in 'biuf':
+        v = v.item() if v.ndim == 0 else tuple(float(x) for x in v)      # e.g. bg_intensity_range
+      else:
+        v = str(v)
       setattr(tgt[cls], attr, v)
   params = {}
   for k in g.files:
@@ -52,6 +55,9 @@ def rand_of(g, mode, n):
   r = {'jitter': [torch.tensor(g[f'rand/jitter{i}']) for i in range(n)]}
   if f'rand/density_noise0' in g.files:
     r['density_noise'] = [torch.tensor(g[f'rand/density_noise{i}']) for i in range(n)]
+  for name in ('bottleneck_noise', 'bg'):           # present only at the levels that draw them
+    if any(f'rand/{name}{i}' in g.files for i in range(n)):
+      r[name] = [torch.tensor(g[f'rand/{name}{i}']) if f'rand/{name}{i}' in g.files else None for i in range(n)]
   return r
 
 
@@ -59,7 +65,7 @@ def rand_of(g, mode, n):
 TOL = dict(atol=2e-5, rtol=2e-4)
 
 
-@pytest.mark.parametrize('tag', ['mini360', 'plumbing', 'miniraw', 'minirefnerf'])
+@pytest.mark.parametrize('tag', ['mini360', 'plumbing', 'miniraw', 'minirefnerf', 'miniglo'])
 @pytest.mark.parametrize('mode', ['det', 'rand'])
 def test_model_apply_matches_reference_run(tag, mode):
   g, b, params, rays, bases = load(tag)
@@ -92,7 +98,7 @@ def test_model_apply_matches_reference_run(tag, mode):
       close(v.detach(), g[f'{mode}/hist{lv}/{k}'], msg=f'{tag} {mode} hist{lv}/{k}', **tol)
 
 
-@pytest.mark.parametrize('tag', ['mini360', 'plumbing', 'miniraw', 'minirefnerf'])
+@pytest.mark.parametrize('tag', ['mini360', 'plumbing', 'miniraw', 'minirefnerf', 'miniglo'])
 def test_losses_and_clip_match_reference_run(tag):
   g, b, params, rays, bases = load(tag)
   n = b.model.num_levels
