@@ -37,12 +37,16 @@ def save_checkpoint(ckpt_dir, state, step, keep=100, model=None):
   p = state.params
   blob = {
       'step': int(step),
-      'layout': {k: tuple(v) for k, v in p.offsets.items()},
+      'layout': {k: tuple(int(x) for x in v) for k, v in p.offsets.items()},
       'params': p.flat.detach().cpu(),
       'opt_state': {'count': int(p.step), 'mu': p.mu.detach().cpu(), 'nu': p.nu.detach().cpu()},
   }
   if model is not None:
-    blob['params_tree'] = model.export_flax()
+    # tensors only (no numpy objects), so the file loads with weights_only=True
+    blob['params_tree'] = {m: {l: {k: torch.from_numpy(v.copy()) for k, v in leaf.items()}
+                               for l, leaf in layers.items()} if m in model.plans else
+                           {k: torch.from_numpy(v.copy()) for k, v in layers.items()}
+                           for m, layers in model.export_flax().items()}
   path = os.path.join(ckpt_dir, f'{PREFIX}{int(step)}')
   tmp = path + '.tmp'
   torch.save(blob, tmp)
@@ -58,7 +62,7 @@ def restore_checkpoint(ckpt_dir, state, step=None, model=None):
   path = latest_checkpoint(ckpt_dir) if step is None else os.path.join(ckpt_dir, f'{PREFIX}{int(step)}')
   if path is None or not os.path.exists(path):
     return state
-  blob = torch.load(path, map_location='cpu', weights_only=False)
+  blob = torch.load(path, map_location='cpu', weights_only=True)   # tensors / ints / tuples only: no pickle code paths
   p = state.params
   layout = {k: tuple(v) for k, v in p.offsets.items()}
   if blob['layout'] != layout:

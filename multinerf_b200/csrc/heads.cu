@@ -259,7 +259,8 @@ grad_norm_kernel(int64_t n, const float* __restrict__ g, float scale, float max_
   float acc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = g[i] * scale;
-    if (max_val > 0.f) v = fminf(fmaxf(v, -max_val), max_val);
+    // jnp.clip propagates NaN (fminf/fmaxf would drop it): a NaN anywhere makes the module norm NaN
+    if (max_val > 0.f && v == v) v = fminf(fmaxf(v, -max_val), max_val);
     acc += v * v;
   }
   acc = warp_sum(acc);
@@ -277,14 +278,20 @@ __global__ void __launch_bounds__(256)
 clip_adam_kernel(mnrf_adam_desc d, float* __restrict__ p, const float* __restrict__ g,
                  float* __restrict__ mu, float* __restrict__ nu, const float* __restrict__ norm_sq,
                  const float* __restrict__ dyn) {
+  // train_utils.py:200-218 then :328: value clip, mult = min(1, max_norm / (eps + norm)), mult * g,
+  // nan_to_num.  jnp.minimum / jnp.clip propagate NaN, so a NaN anywhere in the module makes mult NaN
+  // and the whole module's update zero; an infinite norm gives mult = 0.
   float mult = 1.f;
-  if (d.grad_max_norm > 0.f) mult = fminf(1.f, d.grad_max_norm / (kEps + sqrtf(*norm_sq)));
+  if (d.grad_max_norm > 0.f) {
+    const float nrm = sqrtf(*norm_sq);
+    mult = (nrm != nrm) ? nrm : fminf(1.f, d.grad_max_norm / (kEps + nrm));
+  }
   float bc1 = 1.f - powf(d.beta1, (float)d.step);
   float bc2 = 1.f - powf(d.beta2, (float)d.step);
   if (dyn) { d.lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = g[i] * d.grad_scale;
-    if (d.grad_max_val > 0.f) v = fminf(fmaxf(v, -d.grad_max_val), d.grad_max_val);
+    if (d.grad_max_val > 0.f && v == v) v = fminf(fmaxf(v, -d.grad_max_val), d.grad_max_val);
     v *= mult;
     // jnp.nan_to_num: nan -> 0, +-inf -> +-max float
     if (isnan(v)) v = 0.f;

@@ -203,7 +203,11 @@ class MLPDevice:
                                          for sp in plan.specs], self.device)
     ops.pack_weights_batched(self._pack_table)
     d = plan.one('density')
-    self.colv_density = self.w_nk[d.name][0].float().contiguous()   # bf16-rounded, as the fwd used
+    # bf16-rounded, as the fwd used.  Updated IN PLACE: captured CUDA graphs hold this pointer
+    # (DGRAD colv / outer_mask), so the tensor must never be re-allocated.
+    if getattr(self, 'colv_density', None) is None:
+      self.colv_density = torch.zeros(d.in_pad, device=self.device)
+    self.colv_density.copy_(self.w_nk[d.name][0])
     if plan.ref_stage:
       # [x_pad, vin_pad] K-major B operand of the trunk-entry dgrad:  [ W_bottleneck | head weights ]
       bt = plan.one('bottleneck')

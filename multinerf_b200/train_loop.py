@@ -141,7 +141,7 @@ def train(bundle, dataset, seed=20200823, log=print, use_graph=False):
       if config.checkpoint_dir and rank == 0 and (step == 1 or step % config.checkpoint_every == 0):
         checkpoints.save_checkpoint(config.checkpoint_dir, state, int(step), keep=100, model=model)
     if config.checkpoint_dir and rank == 0 and config.max_steps % config.checkpoint_every != 0:
-      checkpoints.save_checkpoint(config.checkpoint_dir, state, int(state.step), keep=100, model=model)   # train.py:284-287
+      checkpoints.save_checkpoint(config.checkpoint_dir, state, int(config.max_steps), keep=100, model=model)   # train.py:284-287
   finally:
     gc.enable()
   return model, state, history

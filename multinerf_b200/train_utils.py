@@ -94,7 +94,11 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
   stats_buf = torch.zeros(mcfg.num_levels, 8, device=dev)
   scratch = torch.zeros(4, device=dev)
   dyn = torch.zeros(4, device=dev)               # lr, 1-b1^t, 1-b2^t
-  dyn_host = torch.zeros(4).pin_memory() if torch.cuda.is_available() else torch.zeros(4)
+  # Pinned staging ring for the per-step scalars: the host may run several graph replays ahead of the
+  # device, so a slot is rewritten only after the H2D copy that last read it has completed (event).
+  DYN_SLOTS = 8
+  dyn_host = [torch.zeros(4).pin_memory() for _ in range(DYN_SLOTS)]
+  dyn_events = [None] * DYN_SLOTS
   anneal_dev = torch.zeros(1, device=dev)
   G = {'state': 0, 'fb': None, 'opt': None, 'rays': None, 'target': None, 'jitter': None,
        'noise': None, 'launches': 0}
@@ -170,10 +174,17 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       mlp.repack()
 
   def set_dyn(step, lr):
-    dyn_host[0] = lr
-    dyn_host[1] = 1.0 - config.adam_beta1 ** step
-    dyn_host[2] = 1.0 - config.adam_beta2 ** step
-    dyn.copy_(dyn_host, non_blocking=True)
+    slot = G['dyn_slot'] = (G.get('dyn_slot', -1) + 1) % DYN_SLOTS
+    if dyn_events[slot] is not None:
+      dyn_events[slot].synchronize()
+    h = dyn_host[slot]
+    h[0] = lr
+    h[1] = 1.0 - config.adam_beta1 ** step
+    h[2] = 1.0 - config.adam_beta2 ** step
+    dyn.copy_(h, non_blocking=True)
+    if dyn_events[slot] is None:
+      dyn_events[slot] = torch.cuda.Event()
+    dyn_events[slot].record()
 
   def draw_randomness(rng, B, sched):
     """Explicit draws for this step (the reference splits a threefry key per level)."""
@@ -232,7 +243,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       optim(grad_scale, params.step, lr, None)
       G['state'] = 1 if use_graph else 0
       G['B'] = B
-      return state, LazyStats(stats_buf, n), rng
+      return state, LazyStats(stats_buf.clone(), n), rng
     if G['B'] != B:
       raise ValueError(f'graph mode needs a fixed batch size ({G["B"]} rays per rank), got {B}')
     rand = draw_randomness(rng, B, sched)
@@ -270,14 +281,16 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     allreduce_mean_(params.grads, stats_buf, world)
     G['opt'].replay()
     ops.LAUNCHES += G['launches']
-    return state, LazyStats(stats_buf, n), rng
+    return state, LazyStats(stats_buf.clone(), n), rng
 
   train_step.graph_info = G
   return train_step
 
 
 class LazyStats(dict):
-  """Reads the device-side loss accumulators only when asked (no sync in the step)."""
+  """Reads the step's loss accumulators only when asked (no sync in the step).  `buf` is this step's own
+  snapshot of the shared accumulator, so stats kept across steps stay distinct (train.py averages the
+  print window)."""
 
   def __init__(self, buf, n):
     super().__init__()

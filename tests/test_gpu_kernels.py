@@ -288,7 +288,9 @@ def _bf(x):
 @pytest.mark.parametrize('M,N,K', [(128, 256, 64), (256, 256, 512), (1000, 128, 320), (384, 1024, 1536),
                                    (130, 64, 128), (4096, 256, 256), (38000, 256, 64), (10000, 768, 128),
                                    # whole 256-row units: CTA-pair (cta_group::2) variant, several tiles per pair
-                                   (38144, 256, 64), (10240, 1024, 256), (512, 512, 128)])
+                                   (38144, 256, 64), (10240, 1024, 256), (512, 512, 128),
+                                   # CTA pairs at the 360.gin NerfMLP layer shapes (K = 1024 and the skip layer's 1536)
+                                   (512, 1024, 1024), (512, 1024, 1536), (16384, 1024, 512)])
 def test_gemm_fwd(ops, impl, M, N, K):
   from multinerf_b200 import lib as L
   rng = np.random.default_rng(M + N + K)
@@ -318,7 +320,9 @@ def test_gemm_fwd(ops, impl, M, N, K):
                                    # column sums resident in registers (N=768: 3 column blocks, not resident)
                                    (38000, 256, 256), (10000, 1024, 256), (10000, 768, 128),
                                    # CTA-pair variant (M % 256 == 0)
-                                   (37888, 256, 256), (10240, 1024, 256), (10240, 768, 128)])
+                                   (37888, 256, 256), (10240, 1024, 256), (10240, 768, 128),
+                                   # CTA pairs with the long reductions of the 360.gin NerfMLP (K = 1024 / 1536)
+                                   (512, 1024, 1024), (512, 1024, 1536), (16384, 1024, 1024)])
 def test_gemm_dgrad(ops, impl, M, N, K):
   from multinerf_b200 import lib as L
   rng = np.random.default_rng(M + 7 * N + K)
@@ -440,6 +444,26 @@ def test_pack_weights_and_adam(ops):
   ops.clip_adam(pc2, g.cuda(), m.cuda(), v.cuda(), scratch, step=7, lr=1.5e-3, beta1=0.9, beta2=0.999,
                 eps=1e-6, grad_max_val=0.0, grad_max_norm=1e-3)
   assert torch.isfinite(pc2).all()
+  # Reference order (train_utils.py:200-218 then :328): value clip -> norm clip -> nan_to_num.  jnp.clip and
+  # jnp.minimum propagate NaN, so one NaN makes the module's mult NaN and the WHOLE module's gradient 0:
+  # Adam then sees g = 0 everywhere (moments decay, parameters move by the momentum term only).
+  zero = torch.zeros(n)
+  for max_val in (0.0, 0.1):
+    p_z, m_z, v_z = o_train.adam_update(p, zero, m, v, 6, 1.5e-3, Cfg)
+    pc3, mc3, vc3 = p.cuda(), m.cuda(), v.cuda()
+    ops.clip_adam(pc3, g.cuda(), mc3, vc3, scratch, step=7, lr=1.5e-3, beta1=0.9, beta2=0.999, eps=1e-6,
+                  grad_max_val=max_val, grad_max_norm=1e-3)
+    close(pc3, p_z, atol=1e-7, rtol=1e-5, msg='adam p after a NaN gradient (module update zeroed)')
+    close(mc3, m_z, atol=1e-9, rtol=1e-5, msg='adam m after a NaN gradient')
+  # without norm clipping only the NaN element itself is zeroed (nan_to_num), also under a value clip
+  g2 = g.clone()
+  gf2 = torch.nan_to_num(g2).clamp(-1e-3, 1e-3)
+  p_r, m_r, _ = o_train.adam_update(p, gf2, m, v, 6, 1.5e-3, Cfg)
+  pc4, mc4 = p.cuda(), m.cuda()
+  ops.clip_adam(pc4, g2.cuda(), mc4, v.cuda(), scratch, step=7, lr=1.5e-3, beta1=0.9, beta2=0.999, eps=1e-6,
+                grad_max_val=1e-3, grad_max_norm=0.0)
+  close(mc4, m_r, atol=1e-9, rtol=1e-5, msg='adam m, value clip with a NaN element')
+  assert float(mc4[5]) == float(0.9 * m[5])          # NaN -> 0, not -grad_max_val
 
 
 def test_composite_diffuse_specular_mode(ops):

@@ -186,7 +186,7 @@ def test_train_step_vs_oracle(mods, which, impl):
         worst = max(worst, rel)
         # dY travels between layers in bf16 on both sides (different rounding points): the deepest
         # backward path (Dense_0) accumulates the most; measured 0.09 rel / 0.996 cos on B200
-        assert rel < 0.15 and cos > 0.99, (mname, lname, leaf, rel, cos)
+        assert rel < 0.12 and cos > 0.993, (mname, lname, leaf, rel, cos)
   # parameters after one Adam step (first step moves every weight by ~lr regardless of scale)
   newp = model.export_flax()
   lr = o_train.lr_at(0, bundle.config)
@@ -233,6 +233,47 @@ def test_cuda_graph_train_step_matches_eager(mods):
   # fp32 atomics make the two runs differ in the last bits only
   rel = float((p0 - p1).norm() / p0.norm())
   assert rel < 2e-3, rel
+
+
+def test_cuda_graph_gradients_track_eager_with_moving_weights(mods):
+  """Graph replays must read the CURRENT weights everywhere, including the fp32 density-head row the
+  NerfMLP dgrad folds in as a rank-1 term (`colv_density`): with a large learning rate the weights move
+  by tens of percent over a dozen steps, so a pointer captured to a stale copy shows up as a trunk
+  gradient error far above the fp32-atomics noise between the two modes."""
+  models, train_utils = mods
+  from multinerf_b200 import utils
+  bundle = mini360()
+  bundle.config.lr_init = bundle.config.lr_final = 5e-3
+  bundle.config.lr_delay_steps = 0
+  B, steps = 256, 12
+  rays, rng = synth_rays(55, B, 0.2, 1e6)
+  batches = [(synth_rays(60 + i, B, 0.2, 1e6)[0], rng.uniform(0, 1, (B, 3)).astype(np.float32)) for i in range(steps)]
+  rands = [{'jitter': [torch.tensor(rng.uniform(0, 1, (B,)).astype(np.float32)) for _ in range(3)]}
+           for _ in range(steps)]
+  grads, w_density = [], []
+  for use_graph in [False, True]:
+    model, variables = models.construct_model(56, rays, bundle)
+    d = model.plans['NerfMLP_0'].one('density')
+    w0 = model.mlps['NerfMLP_0'].W(d).clone()
+    step_fn = train_utils.create_train_step(model, bundle.config, use_graph=use_graph)
+    state = train_utils.TrainState(variables)
+    for i in range(steps):
+      r, tgt = batches[i]
+      state, stats, _ = step_fn(rands[i], state, utils.Batch(rays=r, rgb=tgt), None, i / 20.0)
+    torch.cuda.synchronize()
+    grads.append(model.export_grads_flax())
+    w1 = model.mlps['NerfMLP_0'].W(d)
+    w_density.append(float((w1 - w0).norm() / w0.norm()))
+    # the fp32 row handed to the dgrad epilogue is the bf16 rounding of the current master weights
+    assert torch.equal(model.mlps['NerfMLP_0'].colv_density,
+                       w1[:, 0].to(torch.bfloat16).float()), 'colv_density is stale'
+  assert min(w_density) > 0.05, w_density        # the head really moved
+  for mname in grads[0]:
+    for lname in grads[0][mname]:
+      a = torch.tensor(grads[0][mname][lname]['kernel']).double().flatten()
+      b = torch.tensor(grads[1][mname][lname]['kernel']).double().flatten()
+      rel = float((a - b).norm() / a.norm().clamp(min=1e-30))
+      assert rel < 2e-2, (mname, lname, rel)
 
 
 def test_rawnerf_train_step_vs_oracle(mods):

@@ -58,7 +58,7 @@ def test_checkpoint_resume(tmp_path):
   # same data and the same Adam state; only the jitter draws after the restart differ
   rel = float((pa - pb).norm() / pa.norm())
   assert rel < 0.05, rel
-  blob = torch.load(checkpoints.latest_checkpoint(ck), map_location='cpu', weights_only=False)
+  blob = torch.load(checkpoints.latest_checkpoint(ck), map_location='cpu', weights_only=True)
   assert blob['step'] == 120 and set(blob['params_tree']) == {'NerfMLP_0', 'PropMLP_0'}
   assert blob['params_tree']['NerfMLP_0']['Dense_0']['kernel'].shape[1] == 128
   with pytest.raises(ValueError):

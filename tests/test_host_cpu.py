@@ -75,6 +75,7 @@ def test_gin_subset_binds_reference_configs():
     same = configs.load_config([os.path.join(ref, '360.gin')])
     assert same == configs.bundle_360()
     assert configs.load_config([os.path.join(ref, 'blender_256.gin')]) == configs.bundle_blender_256()
+    assert r == configs.bundle_blender_refnerf() and raw == configs.bundle_llff_raw()
   b2 = configs.load_config(gin_bindings=['Config.batch_size = 4096', "Model.ray_shape = 'cylinder'",
                                          'NerfMLP.net_activation = @jax.nn.relu', 'Unknown.thing = 3'])
   assert b2.config.batch_size == 4096 and b2.model.ray_shape == 'cylinder' and b2.nerf_mlp.net_activation == 'relu'
