@@ -237,6 +237,8 @@ class LevelState:
 class Params:
   """`variables`: flat fp32 parameter/gradient/Adam buffers + per-module views."""
 
+  STATS_TAIL = 64      # floats: [num_levels, 8] loss accumulators (num_levels <= 8)
+
   def __init__(self, plans: Dict[str, MLPPlan], device, extra: Dict[str, int]):
     self.plans = plans
     self.offsets = {}
@@ -249,7 +251,12 @@ class Params:
       off += (n + 3) // 4 * 4
     self.total = off
     self.flat = torch.zeros(off, device=device)
-    self.grads = torch.zeros(off, device=device)
+    # gradient buffer + a small tail that carries the step's loss statistics, so the data-parallel
+    # exchange of a train step is ONE all-reduce over one flat buffer (pmean of grad and stats,
+    # train_utils.py:319-321)
+    self.grads_ext = torch.zeros(off + self.STATS_TAIL, device=device)
+    self.grads = self.grads_ext[:off]
+    self.stats_tail = self.grads_ext[off:]
     self.mu = torch.zeros(off, device=device)
     self.nu = torch.zeros(off, device=device)
     self.step = 0
@@ -429,9 +436,13 @@ class Model:
 
   # ------------------------------------------------------------------ buffers
   def _level_state(self, key, mname, B, S):
+    # one buffer set per (level, module, shape), never replaced: captured CUDA graphs (train step, render
+    # chunks) hold raw pointers into these buffers, so a differently shaped call (the ragged last chunk of
+    # an image) must not free them
+    key = (key, mname, B, S)
     st = self._levels.get(key)
     plan = self.plans[mname]
-    if st is not None and st.B == B and st.S == S and st.mname == mname:
+    if st is not None:
       return st
     st = LevelState()
     st.B, st.S, st.mname = B, S, mname
@@ -697,9 +708,14 @@ class Model:
     """models.py:75-312.  rng: None (deterministic), a torch.Generator on the device, or a
     dict of explicit draws {'jitter': [per level], 'density_noise': [per level]}."""
     r = self._prep_rays(rays)
-    states = self.forward_levels(rng, r, train_frac, compute_extras, want_samples=True, zero_glo=zero_glo)
     lead = tuple(np.asarray(rays.origins).shape[:-1]) if not isinstance(rays.origins, torch.Tensor) \
         else tuple(rays.origins.shape[:-1])
+    return self.call_prepped(rng, r, lead, train_frac, compute_extras, zero_glo)
+
+  def call_prepped(self, rng, r, lead, train_frac, compute_extras, zero_glo=True):
+    """`__call__` on rays already flattened on the device (`_prep_rays`): device work only, so a render
+    chunk can be captured in a CUDA graph (train_utils.create_render_fn)."""
+    states = self.forward_levels(rng, r, train_frac, compute_extras, want_samples=True, zero_glo=zero_glo)
     renderings, ray_history = [], []
     n_vis = self.config.vis_num_rays
     for st in states:

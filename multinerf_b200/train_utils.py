@@ -91,7 +91,12 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       raise ValueError(f'weight_decay_mults: unknown parameter subtree {key!r}')
     decay_views.append((parts[0], parts[1] if len(parts) == 2 else None, float(mult)))
   dev = model.device
-  stats_buf = torch.zeros(mcfg.num_levels, 8, device=dev)
+  if mcfg.num_levels * 8 > models.Params.STATS_TAIL:
+    raise ValueError(f'num_levels {mcfg.num_levels} > {models.Params.STATS_TAIL // 8}')
+
+  def stats_view(params):
+    # the loss accumulators ride in the tail of the flat gradient buffer: one collective per step
+    return params.stats_tail[:mcfg.num_levels * 8].view(mcfg.num_levels, 8)
   scratch = torch.zeros(4, device=dev)
   dyn = torch.zeros(4, device=dev)               # lr, 1-b1^t, 1-b2^t
   # Pinned staging ring for the per-step scalars: the host may run several graph replays ahead of the
@@ -102,21 +107,37 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
   anneal_dev = torch.zeros(1, device=dev)
   G = {'state': 0, 'fb': None, 'opt': None, 'rays': None, 'target': None, 'jitter': None,
        'noise': None, 'launches': 0}
+  import os
+  GRAPH_NCCL = os.environ.get('MNRF_GRAPH_NCCL', '1') != '0'
 
-  def fwd_bwd(rng, rays, target, train_frac, anneal_ptr):
+  # Backward runs the levels last to first, so a module's gradient is final once the lowest level that
+  # uses it is done: for 360.gin the NerfMLP segment (34.7 of 36 MB) is final after level 2 and its
+  # all-reduce overlaps the two PropMLP backward levels.
+  def early_segments(n_levels):
+    if decay_views:
+      return {}                      # weight decay touches every gradient after the last level
+    first_use = {}
+    for i in range(n_levels):
+      mname = 'NerfMLP_0' if (mcfg.single_mlp or i == n_levels - 1) else 'PropMLP_0'
+      first_use.setdefault(mname, i)
+    return {i: mname for mname, i in first_use.items() if i > 0}
+
+  def fwd_bwd(rng, rays, target, train_frac, anneal_ptr, world=1):
     params = model.params
+    stats_buf = stats_view(params)
     lossmult = rays.lossmult
     if config.disable_multiscale_loss:
       lossmult = torch.ones_like(lossmult)
     lm_ch = lossmult.shape[-1]
     inv_denom = (1.0 / (lossmult.sum() * (3 if lm_ch == 1 else 1))).reshape(1)
-    params.grads.zero_()
-    stats_buf.zero_()
+    params.grads_ext.zero_()
     states = model.forward_levels(rng if config.randomized else None, rays, train_frac,
                                   compute_extras=False, want_samples=False, impl=impl,
                                   anneal_dev=anneal_ptr, loss_config=config, zero_glo=False)
     fine = states[-1]
     n = len(states)
+    early = early_segments(n) if world > 1 else {}
+    pending, reduced = [], []
     for i in range(n - 1, -1, -1):
       st = states[i]
       is_fine = i == n - 1
@@ -141,8 +162,21 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
         params.seg('exposure_scaling_offsets', params.grads).view(-1, 3).index_add_(0, eidx, g)
       model._mlp_backward(st, model.mlps[st.mname], rays=rays, impl=impl, loss_mults=st.loss_mults,
                           stats=stats_buf[i])
+      if i in early:
+        o, cnt = params.offsets[early[i]]
+        pending.append(dist.all_reduce(params.grads_ext[o:o + cnt], op=dist.ReduceOp.SUM, async_op=True))
+        reduced.append((o, o + cnt))
     if decay_views:
       weight_decay()
+    if world > 1:
+      # everything not yet exchanged (contiguous ranges of the flat buffer, stats tail included)
+      pos = 0
+      for lo, hi in sorted(reduced) + [(params.grads_ext.numel(), params.grads_ext.numel())]:
+        if lo > pos:
+          dist.all_reduce(params.grads_ext[pos:lo], op=dist.ReduceOp.SUM)
+        pos = hi
+      for w in pending:
+        w.wait()
 
   def weight_decay():
     # loss += mult * sum(w^2)  ->  grad += 2 mult w ; the loss value goes to stats row 0, slot 6
@@ -153,7 +187,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
         if lname is None or sp.name == lname:
           for view_p, view_g in ((mlp.W(sp), mlp.W(sp, mlp.grads)), (mlp.b(sp), mlp.b(sp, mlp.grads))):
             view_g.add_(view_p, alpha=2.0 * mult)
-            stats_buf[0, 6] += mult * (view_p * view_p).sum()
+            stats_view(params)[0, 6] += mult * (view_p * view_p).sum()
 
   def _d_scale_buf(st):
     if st.rgb_scale is None:
@@ -238,12 +272,11 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
                              config.lr_delay_steps, config.lr_delay_mult)
     if not use_graph or G['state'] == 0:
       # eager step (also the warm-up that allocates every buffer before a capture)
-      fwd_bwd(draw_randomness(rng, B, sched) if use_graph else rng, rays, target, train_frac, None)
-      allreduce_mean_(params.grads, stats_buf, world)
+      fwd_bwd(draw_randomness(rng, B, sched) if use_graph else rng, rays, target, train_frac, None, world)
       optim(grad_scale, params.step, lr, None)
       G['state'] = 1 if use_graph else 0
       G['B'] = B
-      return state, LazyStats(stats_buf.clone(), n), rng
+      return state, LazyStats(stats_view(params).clone(), n, grad_scale), rng
     if G['B'] != B:
       raise ValueError(f'graph mode needs a fixed batch size ({G["B"]} rays per rank), got {B}')
     rand = draw_randomness(rng, B, sched)
@@ -260,12 +293,23 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       G['target'] = target.clone()
       torch.cuda.synchronize()
       before = ops.LAUNCHES
-      G['fb'] = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(G['fb']):
-        fwd_bwd(rand, G['rays'], G['target'], train_frac, anneal_dev)
-      G['opt'] = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(G['opt']):
-        optim(grad_scale, params.step, lr, dyn)
+      if world > 1 and not GRAPH_NCCL:
+        # two graphs around eager NCCL calls
+        G['fb'] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(G['fb']):
+          fwd_bwd(rand, G['rays'], G['target'], train_frac, anneal_dev, 1)
+        G['opt'] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(G['opt']):
+          optim(grad_scale, params.step, lr, dyn)
+      else:
+        # ONE graph for the whole step: forward, backward, the gradient all-reduce(s) (NCCL kernels are
+        # captured on their own stream, so the NerfMLP exchange overlaps the PropMLP backward as a parallel
+        # branch of the graph), clip + Adam + weight repack
+        G['fb'] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(G['fb']):
+          fwd_bwd(rand, G['rays'], G['target'], train_frac, anneal_dev, world)
+          optim(grad_scale, params.step, lr, dyn)
+        G['opt'] = None
       G['launches'] = ops.LAUNCHES - before
       G['state'] = 2
     else:
@@ -278,10 +322,11 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
         getattr(G['rays'], extra).copy_(getattr(rays, extra), non_blocking=True)
       G['target'].copy_(target, non_blocking=True)
     G['fb'].replay()
-    allreduce_mean_(params.grads, stats_buf, world)
-    G['opt'].replay()
+    if G['opt'] is not None:
+      allreduce_flat_(params, world)
+      G['opt'].replay()
     ops.LAUNCHES += G['launches']
-    return state, LazyStats(stats_buf.clone(), n), rng
+    return state, LazyStats(stats_view(params).clone(), n, grad_scale), rng
 
   train_step.graph_info = G
   return train_step
@@ -292,12 +337,12 @@ class LazyStats(dict):
   snapshot of the shared accumulator, so stats kept across steps stay distinct (train.py averages the
   print window)."""
 
-  def __init__(self, buf, n):
+  def __init__(self, buf, n, scale=1.0):
     super().__init__()
-    self._buf, self._n = buf, n
+    self._buf, self._n, self._scale = buf, n, scale
 
   def materialize(self):
-    b = self._buf.detach().cpu()
+    b = self._buf.detach().cpu() * self._scale       # pmean of the per-rank stats: SUM all-reduce x 1/world
     mses = b[:, 1].clone()
     losses = {'data': float(b[:, 0].sum()), 'interlevel': float(b[:, 3].sum()),
               'distortion': float(b[:, 2].sum()), 'orientation': float(b[:, 4].sum()),
@@ -310,24 +355,42 @@ class LazyStats(dict):
     return self
 
 
-def gather_renderings(renderings, world):
-  """all_gather of every per-pixel buffer (lax.all_gather, train_utils.py:380-388); `ray_*`
-  visualisation bundles stay local.  Rank r's rows land at [r*n, (r+1)*n)."""
+def gather_renderings(renderings, world, all_levels=False):
+  """all_gather of the per-pixel buffers (lax.all_gather, train_utils.py:380-388) as ONE collective per
+  chunk: the per-pixel outputs of a level are packed into one [rays, C] fp32 buffer, gathered with a
+  single all_gather_into_tensor and unpacked (rank r's rows land at [r*n, (r+1)*n)).  `ray_*`
+  visualisation bundles stay local.  The reference gathers every level and render_image then keeps
+  only the last one (models.py:689-694); here only the last level travels unless `all_levels`."""
   if world <= 1:
     return renderings
   out = []
-  for r in renderings:
-    g = {}
-    for k, v in r.items():
-      if k.startswith('ray_'):
-        g[k] = v
-        continue
-      v = v.contiguous()
-      buf = torch.empty((world * v.shape[0],) + tuple(v.shape[1:]), device=v.device, dtype=v.dtype)
-      dist.all_gather_into_tensor(buf, v)
-      g[k] = buf
+  for i, r in enumerate(renderings):
+    if not all_levels and i != len(renderings) - 1:
+      out.append({k: v for k, v in r.items() if k.startswith('ray_')})
+      continue
+    keys = [k for k in r if not k.startswith('ray_')]
+    g = {k: v for k, v in r.items() if k.startswith('ray_')}
+    if keys:
+      n = r[keys[0]].shape[0]
+      cols = [r[k].reshape(n, -1).to(torch.float32) for k in keys]
+      widths = [c.shape[1] for c in cols]
+      packed = torch.cat(cols, 1).contiguous()
+      buf = torch.empty(world * n, packed.shape[1], device=packed.device, dtype=packed.dtype)
+      dist.all_gather_into_tensor(buf, packed)
+      c0 = 0
+      for k, w in zip(keys, widths):
+        g[k] = buf[:, c0:c0 + w].reshape((world * n,) + tuple(r[k].shape[1:])).to(r[k].dtype)
+        c0 += w
     out.append(g)
   return out
+
+
+def allreduce_flat_(params, world):
+  """pmean of gradients and stats as ONE collective over the flat buffer (gradients + stats tail); the
+  1/world factor is applied downstream (clip_adam grad_scale, LazyStats scale)."""
+  if world > 1:
+    dist.all_reduce(params.grads_ext, op=dist.ReduceOp.SUM)
+  return 1.0 / world
 
 
 def allreduce_mean_(grads, stats, world):
@@ -341,16 +404,59 @@ def allreduce_mean_(grads, stats, world):
   return 1.0 / world
 
 
-def create_render_fn(model: models.Model):
+def create_render_fn(model: models.Model, use_graph=False):
   """render_eval_pfn(variables, train_frac, _, rays): deterministic render of this rank's rays,
-  with the per-rank pixel buffers all-gathered (train_utils.py:377-396)."""
+  with the per-rank pixel buffers all-gathered (train_utils.py:377-396).
+
+  use_graph=True replays one captured CUDA graph per (chunk size, train_frac): a full image is ~100 chunks
+  of the same shape, and at 8 GPUs a 16384-ray chunk leaves 2048 rays per rank, where the ~45 launches of
+  a forward pass cost more host time than device time.  Ragged chunks (the last one) run eagerly."""
+  import dataclasses
+  G = {}
 
   def render_eval_fn(variables, train_frac, _, rays):
     world, rank = _world()
-    renderings, ray_history = model.apply(variables, None, rays, train_frac=train_frac,
-                                          compute_extras=True)
-    renderings = gather_renderings(renderings, world)
-    return renderings, ray_history
+    if variables is not model.params:
+      model.bind(variables)
+      G.clear()
+    if not use_graph:
+      renderings, ray_history = model.apply(variables, None, rays, train_frac=train_frac, compute_extras=True)
+      return gather_renderings(renderings, world), ray_history
+    r = model._prep_rays(rays)
+    B = r.origins.shape[0]
+    lead = tuple(rays.origins.shape[:-1])
+    key = (B, float(train_frac), lead)
+    ent = G.get(key)
+    if ent is None:
+      # first sight of this shape: eager (allocates the level buffers); capture on the second
+      G[key] = {'graph': None}
+      renderings, ray_history = model.call_prepped(None, r, lead, train_frac, True)
+      return gather_renderings(renderings, world), ray_history
+    fields = [f.name for f in dataclasses.fields(r) if getattr(r, f.name) is not None] + \
+        ['radii_flat', 'near_flat', 'far_flat']
+    if ent['graph'] is None:
+      ent['rays'] = type(r)(**{f.name: (None if getattr(r, f.name) is None else getattr(r, f.name).clone())
+                               for f in dataclasses.fields(r)})
+      for extra in ('radii_flat', 'near_flat', 'far_flat'):
+        setattr(ent['rays'], extra, getattr(r, extra).clone())
+      torch.cuda.synchronize()
+      before = ops.LAUNCHES
+      ent['graph'] = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(ent['graph']):
+        ent['out'] = model.call_prepped(None, ent['rays'], lead, train_frac, True)
+      ent['launches'] = ops.LAUNCHES - before
+    else:
+      for name in fields:
+        getattr(ent['rays'], name).copy_(getattr(r, name), non_blocking=True)
+    ent['graph'].replay()
+    ops.LAUNCHES += ent['launches']
+    renderings, ray_history = ent['out']
+    # static output buffers are overwritten by the next replay: hand out copies of what render_image keeps
+    # (the last level's pixels -- for world > 1 the gather itself copies them -- and the ray_* bundles)
+    last = len(renderings) - 1
+    renderings = [{k: (v.clone() if (world == 1 or k.startswith('ray_')) else v) for k, v in rr.items()
+                   if i == last or k.startswith('ray_')} for i, rr in enumerate(renderings)]
+    return gather_renderings(renderings, world), ray_history
 
   return render_eval_fn
 

@@ -195,6 +195,18 @@ def _gloo_worker(rank, world, port, q):
   rend = [{'rgb': torch.full((4, 3), float(rank)), 'acc': torch.arange(4.) + 10 * rank,
            'ray_sdist': torch.full((2, 5), float(rank))}]
   g = train_utils.gather_renderings(rend, world)
+  # two levels: only the last one travels (render_image keeps nothing else), ray_* bundles stay local
+  two = train_utils.gather_renderings([dict(rend[0]), dict(rend[0])], world)
+  assert set(two[0]) == {'ray_sdist'} and two[1]['rgb'].shape == (8, 3)
+  assert train_utils.gather_renderings([dict(rend[0]), dict(rend[0])], world, all_levels=True)[0]['acc'].shape == (8,)
+  # the train step's single flat exchange: gradients + the stats tail in one all-reduce
+  from multinerf_b200 import configs, models
+  b = configs.bundle_blender_256()
+  prm = models.Params({'NerfMLP_0': models.MLPPlan(b.nerf_mlp, True)}, 'cpu', {})
+  prm.grads.fill_(float(rank + 1))
+  prm.stats_tail.fill_(float(rank))
+  assert train_utils.allreduce_flat_(prm, world) == 0.5
+  assert float(prm.grads.min()) == float(prm.grads.max()) == 3.0 and float(prm.stats_tail.max()) == 1.0
   q.put((rank, grads.tolist(), stats[0, 0].item(), scale, g[0]['rgb'][:, 0].tolist(), g[0]['acc'].tolist(),
          g[0]['ray_sdist'][0, 0].item()))
   dist.destroy_process_group()
