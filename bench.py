@@ -30,7 +30,7 @@ import time
 # magnitude, so that arm resets the variables before numpy / torch are imported.
 # CPU_THREADS: pinned from the thread sweep of tools/cpu_sweep.py on the GPU box's host
 # (profiles/r02_cpu_sweep.txt): the torch-CPU graph of many small ops stops scaling past this count.
-CPU_THREADS_DEFAULT = 32
+CPU_THREADS_DEFAULT = 16
 if '--impl' in sys.argv and sys.argv[sys.argv.index('--impl') + 1:sys.argv.index('--impl') + 2] == ['reference'] \
     or '--impl=reference' in sys.argv:
   _t = str(min(os.cpu_count() or 1, int(os.environ.get('MNRF_CPU_THREADS', str(CPU_THREADS_DEFAULT)))))
@@ -171,7 +171,7 @@ def peaks():
 
 class ClockSampler:
   """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started early
-  (nvidia-smi takes about a second to produce its first line) and polls every 20 ms; `window()` marks the
+  (nvidia-smi takes about a second to produce its first line) and polls every 25 ms; `window()` marks the
   host-time interval of the timed region and only samples inside it are reported, so even a 0.1 s region
   (8 GPUs) carries clock evidence."""
   Q = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -189,7 +189,7 @@ class ClockSampler:
       fd, self.path = tempfile.mkstemp(suffix='.csv')
       os.close(fd)
       self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                    '-lms', '20', '-i', str(self.idx)],
+                                    '-lms', '25', '-i', str(self.idx)],
                                    stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
     except Exception:  # pylint: disable=broad-except
       self.proc = None
@@ -351,8 +351,10 @@ def run_ours(args):
   sampler.window(*win)
   launches_total = ops.LAUNCHES                 # our kernels launched inside the timed region (all K steps)
   launches = launches_total // max(1, args.steps)
-  ms_e2e, loss_host, _ = timed(args.steps, True)
+  # stop the poller before the end-to-end loop: nvidia-smi queries contend with the driver calls of a loop
+  # that synchronises every step (D2H read of the losses)
   clocks = sampler.stop() if rank == 0 else {}
+  ms_e2e, loss_host, _ = timed(args.steps, True)
 
   # dominant kernel (tcgen05 GEMM, all three modes): CUDA events around every launch of one
   # extra step; achieved = canonical train FLOPs of the step / time spent inside the GEMMs
@@ -441,8 +443,8 @@ def run_render(args, wl, bundle, fwd_flop_ray, world, rank, dev, sampler, barrie
   ms, _, out, win = timed(args.steps, False)
   sampler.window(*win)
   launches_total = ops.LAUNCHES
-  ms_e2e, img, _, _ = timed(args.steps, True)
   clocks = sampler.stop() if rank == 0 else {}
+  ms_e2e, img, _, _ = timed(args.steps, True)
   # GEMM time of one eager chunk (this rank's shard)
   per = chunk // world
   one = dev_rays.map(lambda a: a.reshape(H * W, -1)[:per])
@@ -539,8 +541,8 @@ def cpu_baseline(workload, n_rays, steps, warmup):
   what = 'deterministic render (Model.__call__, compute_extras)' if wl['kind'] == 'render' else 'train step'
   return {'value': n_rays / t, 'unit': 'rays/s', 'cores': threads, 'host_cores': cores, 'kind': 'port',
           'sample': f'{n_rays} rays of the same {wl["bundle"][7:]} {what}, fp32 torch-CPU, '
-                    f'{steps} timed step(s) after {warmup} warm-up, {threads} threads (best of the 16/32/64/128 '
-                    'sweep in profiles/r02_cpu_sweep.txt); CPU restatement of the reference '
+                    f'{steps} timed step(s) after {warmup} warm-up, {threads} threads (the best point of the thread sweep in '
+                    'profiles/r02_cpu_sweep.txt: 16 > 32 > 64 >> 128 on the 128-core host); CPU restatement of the reference '
                     '(JAX/Flax are not installable in this image)',
           's_per_step': t}
 

@@ -14,7 +14,12 @@
  *  - return 0 on success, non-zero on error; the message is in mnrf_last_error()
  *    (thread-local).  Python-side config errors of the reference (ValueError at trace
  *    time) stay Python-side; the ABI reports shape / alignment / launch failures;
- *  - bf16 buffers are raw uint16 storage (`mnrf_bf16`).
+ *  - bf16 buffers are raw uint16 storage (`mnrf_bf16`);
+ *  - WORKSPACE POLICY: no entry needs scratch beyond its declared arguments (every intermediate is an
+ *    argument the caller allocates: per-level activation / mask / gradient buffers are sized from the
+ *    shapes documented per entry), so there are no `*_workspace_bytes` queries; kernels keep their
+ *    staging in shared memory / TMEM.  The Python host (multinerf_b200/models.py `_level_state`)
+ *    allocates each buffer once per (level, shape) and never frees it while a captured graph lives.
  */
 #ifndef MNRF_H_
 #define MNRF_H_
@@ -149,6 +154,62 @@ typedef struct {
 int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
               const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
               float* colsum, const mnrf_bf16* addend, void* out, mnrf_stream stream);
+
+/* ---- layer-chained 256-wide MLP trunk ------------------------------------------------------
+ * ONE persistent launch walks 512-row units of samples through all Dense layers of a 256-wide trunk
+ * (forward; models.py:441-465 incl. the skip concat) or through its whole input-gradient chain
+ * (backward, the dgrad side of jax.value_and_grad, train_utils.py:316-317).  Activations stay in
+ * shared memory between layers and are written out once per layer (for the weight-gradient GEMMs);
+ * accumulators live in TMEM; weights stream from L2 (csrc/chain.cu).
+ *
+ * A layer multiplies up to two operands, both in 64-column k-blocks:
+ *   resident  -- the previous layer's output held in shared memory: n_res = 4 k-blocks (0 for the
+ *                first layer), against weight k-blocks [res_kb0, res_kb0 + 4);
+ *   streamed  -- n_stream k-blocks of the `stream` tensor (columns stream_col0 + 64 s), against weight
+ *                k-blocks [stream_kb0, stream_kb0 + n_stream): the IPE features of layer 0 and of a
+ *                skip layer (forward), the incoming gradient of the first chained layer (backward).
+ * `w` is K-major [256, ldw] bf16: the forward operand w_nk [out, in_pad] or the dgrad operand
+ * w_kn [in_pad(first 256 rows used), out].
+ *   FWD: out = relu(acc + bias) (bf16), maskbits written (1 bit per output, as mnrf_gemm);
+ *        head_w/head_b/head_out (optional): head_out[m] = <bf16(out_last[m, :]), head_w> + head_b[0],
+ *        the Dense(1) density head of models.py:460 computed in the last layer's epilogue.
+ *   BWD: out = acc masked by maskbits (read; NULL = no mask); colsum[256] += column sums of out (the
+ *        bias gradient of the layer whose activation the mask came from).
+ * `out` may be NULL (FWD only: the activation is not needed later).  m is any row count; rows past m
+ * are zero-filled on load and clipped on store.
+ */
+#define MNRF_CHAIN_MAX_LAYERS 8
+enum { MNRF_CHAIN_FWD = 0, MNRF_CHAIN_BWD = 1 };
+
+typedef struct {
+  const mnrf_bf16* w;
+  int64_t ldw;
+  const float* bias;
+  uint32_t* maskbits;
+  int64_t ldmaskbits;         /* in 32-bit words */
+  float* colsum;
+  mnrf_bf16* out;
+  int64_t ldo;
+  int32_t n_stream, stream_col0, stream_kb0;
+  int32_t n_res, res_kb0;
+  int32_t reserved;
+} mnrf_chain_layer;
+
+typedef struct {
+  int32_t mode, num_layers;
+  int32_t width;              /* must be 256 */
+  int32_t stream_cols;        /* columns of `stream` (multiple of 64) */
+  int64_t m;                  /* sample rows */
+  const mnrf_bf16* stream;    /* [m, ldstream] bf16 */
+  int64_t ldstream;
+  const float* head_w;        /* [256] fp32 or NULL */
+  const float* head_b;        /* device scalar or NULL */
+  float* head_out;            /* [m] fp32 */
+  mnrf_chain_layer layer[MNRF_CHAIN_MAX_LAYERS];
+} mnrf_chain_desc;
+
+int mnrf_mlp_chain(const mnrf_chain_desc* d, mnrf_stream stream);
+int mnrf_mlp_chain_max_layers(void);
 
 /* ---- small heads (N <= 4 outputs): density / rgb / predicted normals ---------------------
  * raw[M, n_out] = X[M, K](bf16) * W[n_out, K](bf16) + b, fp32 accumulate; models.py:460,585.

@@ -18,7 +18,7 @@ if os.environ.get('MNRF_TIMING_KNOBS') == '1':      # tools/gemm_variants.sh: ma
 # GEMM and reduction kernels keep FMA.
 SOURCES = {
     'lib.cu': [], 'sampling.cu': ['-fmad=false'], 'encode.cu': ['-fmad=false'],
-    'composite.cu': ['-fmad=false'], 'heads.cu': [], 'gemm_tc.cu': [], 'gemm_ref.cu': [],
+    'composite.cu': ['-fmad=false'], 'heads.cu': [], 'gemm_tc.cu': [], 'chain.cu': [], 'gemm_ref.cu': [],
     'refnerf.cu': [], 'camera.cu': ['-fmad=false'],
 }
 
@@ -32,7 +32,8 @@ def _nvcc():
 
 def _stamp(path, flags):
   h = hashlib.sha1()
-  for p in [path, os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, '..', 'include', 'mnrf.h')]:
+  for p in [path, os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'tc_common.cuh'),
+            os.path.join(HERE, '..', 'include', 'mnrf.h')]:
     with open(p, 'rb') as f:
       h.update(f.read())
   h.update(' '.join(flags).encode())

@@ -75,6 +75,23 @@ class PackItem(C.Structure):
               ('out', C.c_int32), ('tile0', C.c_int32), ('reserved', C.c_int32)]
 
 
+CHAIN_MAX_LAYERS = 8
+CHAIN_FWD, CHAIN_BWD = 0, 1
+
+
+class ChainLayer(C.Structure):
+  _fields_ = [('w', C.c_void_p), ('ldw', C.c_int64), ('bias', C.c_void_p), ('maskbits', C.c_void_p),
+              ('ldmaskbits', C.c_int64), ('colsum', C.c_void_p), ('out', C.c_void_p), ('ldo', C.c_int64),
+              ('n_stream', C.c_int32), ('stream_col0', C.c_int32), ('stream_kb0', C.c_int32),
+              ('n_res', C.c_int32), ('res_kb0', C.c_int32), ('reserved', C.c_int32)]
+
+
+class ChainDesc(C.Structure):
+  _fields_ = [('mode', C.c_int32), ('num_layers', C.c_int32), ('width', C.c_int32), ('stream_cols', C.c_int32),
+              ('m', C.c_int64), ('stream', C.c_void_p), ('ldstream', C.c_int64), ('head_w', C.c_void_p),
+              ('head_b', C.c_void_p), ('head_out', C.c_void_p), ('layer', ChainLayer * CHAIN_MAX_LAYERS)]
+
+
 class AdamDesc(C.Structure):
   _fields_ = [('n', C.c_int64), ('grad_max_val', C.c_float), ('grad_max_norm', C.c_float),
               ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
@@ -101,6 +118,8 @@ _SIGNATURES = {
     'mnrf_viewdir_enc': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),
     'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 11),
+    'mnrf_mlp_chain': (C.c_int, [C.POINTER(ChainDesc), _P]),
+    'mnrf_mlp_chain_max_layers': (C.c_int, []),
     'mnrf_head_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P, _P]),
     'mnrf_head_bwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P,
                                 C.c_int64, C.c_int32, _P, _P, _P, _P]),

@@ -365,6 +365,8 @@ class Model:
     self.params = params
     self.mlps = {n: MLPDevice(p, params.seg(n), params.seg(n, params.grads), self.device)
                  for n, p in self.plans.items()}
+    for st in self._levels.values():        # cached chain descriptors point into the previous buffers
+      st.__dict__.pop('_chain', None)
 
   def export_flax(self):
     """Parameters as the reference's flax tree (numpy), dropping the padding rows."""
@@ -502,6 +504,7 @@ class Model:
           st.roughness = torch.empty(M, device=dev)
         st.extra_dw = torch.empty(B, S, device=dev)
     st.bwd = None   # backward scratch, allocated on first backward
+    st.keep_acts = True     # False: render-only pass, the chained trunk skips activation / mask stores
     self._levels[key] = st
     return st
 
@@ -536,13 +539,21 @@ class Model:
       c.copy_(st.feat)
     x = st.feat
     trunk = plan.by_role('trunk')
-    for i, sp in enumerate(trunk):
-      ops.gemm(L.GEMM_FWD, x, mlp.w_nk[sp.name], st.acts[i][:, :W], m=M, n=W, k=sp.in_pad, act=L.ACT_RELU,
-               bias=mlp.b(sp), maskbits=st.bits[i], impl=impl)
-      x = st.acts[i]          # full width (incl. concatenated features) feeds the next layer
-    st.x_last = x
     d = plan.one('density')
-    ops.head_fwd(x, mlp.w_nk[d.name], mlp.b(d), 1, d.in_pad, raw=st.raw_density.view(M, 1))
+    chained = self._use_chain(plan, M, impl)
+    if chained:
+      # the whole trunk (+ the Dense(1) density head when it reads the plain 256-wide output) in ONE launch
+      ops.mlp_chain(self._chain_fwd_desc(st, mlp))
+      x = st.acts[-1]
+      if plan.last_has_feat:
+        ops.head_fwd(x, mlp.w_nk[d.name], mlp.b(d), 1, d.in_pad, raw=st.raw_density.view(M, 1))
+    else:
+      for i, sp in enumerate(trunk):
+        ops.gemm(L.GEMM_FWD, x, mlp.w_nk[sp.name], st.acts[i][:, :W], m=M, n=W, k=sp.in_pad, act=L.ACT_RELU,
+                 bias=mlp.b(sp), maskbits=st.bits[i], impl=impl)
+        x = st.acts[i]          # full width (incl. concatenated features) feeds the next layer
+      ops.head_fwd(x, mlp.w_nk[d.name], mlp.b(d), 1, d.in_pad, raw=st.raw_density.view(M, 1))
+    st.x_last = x
     if plan.density_normals:
       # raw_grad_density = d raw_density / d mean by forward mode (replaces vmap(value_and_grad),
       # models.py:473-492): tangents see the same weights, no bias, and the primal's ReLU masks
@@ -594,6 +605,70 @@ class Model:
     r = plan.one('rgb')
     ops.head_fwd(v, mlp.w_nk[r.name], mlp.b(r), r.out_dim, r.in_pad, raw=st.raw_rgb.view(M, 3))
 
+  # ------------------------------------------------------------------ layer-chained 256-wide trunks
+  def _use_chain(self, plan, M, impl=0):
+    """One persistent launch per trunk (csrc/chain.cu) when every trunk layer is 256 wide."""
+    import os
+    if impl != 0 or os.environ.get('MNRF_CHAIN', '1') == '0':
+      return False
+    cfg = plan.cfg
+    return (cfg.net_width == 256 and cfg.net_depth <= L.CHAIN_MAX_LAYERS and M >= 512 and
+            plan.Fpad % 64 == 0)
+
+  def _chain_fwd_desc(self, st, mlp):
+    key = ('fwd', st.keep_acts)
+    cache = st.__dict__.setdefault('_chain', {})
+    if key in cache:
+      return cache[key]
+    plan = mlp.plan
+    W = plan.cfg.net_width
+    M = st.B * st.S
+    nf = plan.Fpad // 64
+    trunk = plan.by_role('trunk')
+    layers = []
+    for i, sp in enumerate(trunk):
+      ly = dict(w=mlp.w_nk[sp.name], bias=mlp.b(sp))
+      if i == 0:
+        ly.update(n_stream=nf, stream_col0=0, stream_kb0=0)
+      else:
+        ly.update(n_res=W // 64, res_kb0=0)
+        if sp.in_pad == W + plan.Fpad:          # skip layer: [hidden | features] against [W | Fpad] weight columns
+          ly.update(n_stream=nf, stream_col0=0, stream_kb0=W // 64)
+      last = i == len(trunk) - 1
+      if st.keep_acts or (last and (plan.has_rgb or plan.last_has_feat)):
+        ly['out'] = st.acts[i][:, :W]
+      if st.keep_acts:
+        ly['maskbits'] = st.bits[i]
+      layers.append(ly)
+    head = {}
+    if not plan.last_has_feat:
+      dsp = plan.one('density')
+      head = dict(head_w=mlp.colv_density, head_b=mlp.b(dsp), head_out=st.raw_density.view(M))
+    cache[key] = ops.chain_desc(L.CHAIN_FWD, M, layers, stream=st.feat, stream_cols=plan.Fpad, **head)
+    return cache[key]
+
+  def _chain_bwd_desc(self, st, mlp, dyl):
+    """dyl[i] = gradient w.r.t. the (pre-activation-masked) output of trunk layer i; dyl[-1] is the input."""
+    cache = st.__dict__.setdefault('_chain', {})
+    if 'bwd' in cache:
+      return cache['bwd']
+    plan = mlp.plan
+    W = plan.cfg.net_width
+    M = st.B * st.S
+    trunk = plan.by_role('trunk')
+    g = mlp.grads
+    layers = []
+    for j, i in enumerate(range(len(trunk) - 1, 0, -1)):
+      sp = trunk[i]
+      ly = dict(w=mlp.w_kn[sp.name], maskbits=st.bits[i - 1], colsum=mlp.b(trunk[i - 1], g), out=dyl[i - 1])
+      if j == 0:
+        ly.update(n_stream=W // 64, stream_col0=0, stream_kb0=0)
+      else:
+        ly.update(n_res=W // 64, res_kb0=0)
+      layers.append(ly)
+    cache['bwd'] = ops.chain_desc(L.CHAIN_BWD, M, layers, stream=dyl[-1], stream_cols=W)
+    return cache['bwd']
+
   def _prep_rays(self, rays):
     r = utils.to_device_flat(rays, self.device)
     r.radii_flat = r.radii[:, 0].contiguous()
@@ -641,6 +716,8 @@ class Model:
       st = self._level_state(i, mname, B, lv['S'])
       st.lv = lv
       st.is_prop = lv['is_prop']
+      # activations and ReLU masks are kept for a backward pass (and for the Ref-NeRF tangent chain)
+      st.keep_acts = loss_config is not None or mlp.plan.density_normals
       jit = None
       if rng is not None:
         if isinstance(rng, dict):
@@ -770,7 +847,9 @@ class Model:
     bf = torch.bfloat16
     if st.bwd is None:
       bw_ = LevelState()
-      bw_.dy = [torch.empty(M, W, device=dev, dtype=bf) for _ in range(2)]
+      # per-layer gradient buffers when the dgrad chain runs as one launch (its wgrads come after)
+      n_dy = cfg.net_depth if self._use_chain(plan, M, impl) else 2
+      bw_.dy = [torch.empty(M, W, device=dev, dtype=bf) for _ in range(n_dy)]
       if plan.has_rgb:
         Wv = cfg.net_width_viewdirs
         bw_.dv = [torch.empty(M, Wv, device=dev, dtype=bf) for _ in range(2)]
@@ -881,6 +960,16 @@ class Model:
           ops.gemm(L.GEMM_DGRAD, hcur, mlp.w_kn[sp.name], hoth, m=3 * M, n=W, k=W,
                    maskbits=st.bits[i - 1], mask_mod=M, impl=impl)
           hcur, hoth = hoth, hcur
+    if self._use_chain(plan, M, impl) and len(trunk) > 1:
+      # dyl[i] = d loss / d (output of trunk layer i); dyl[-1] was produced above (sc.dy[0])
+      nl = len(trunk)
+      dyl = [sc.dy[nl - 1 - i] for i in range(nl)]        # dyl[nl-1] is sc.dy[0]
+      ops.mlp_chain(self._chain_bwd_desc(st, mlp, dyl))
+      for i in range(nl - 1, -1, -1):
+        sp = trunk[i]
+        xin = st.feat if i == 0 else st.acts[i - 1]
+        ops.gemm(L.GEMM_WGRAD, xin, dyl[i], mlp.W(sp, g), m=sp.in_pad, n=W, k=M, impl=impl)
+      return
     cur, other = sc.dy[0], sc.dy[1]
     for i in range(len(trunk) - 1, -1, -1):
       sp = trunk[i]

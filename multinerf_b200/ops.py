@@ -149,6 +149,59 @@ def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv
   return out
 
 
+CHAIN_EVENTS_FLOPS = True
+
+
+def chain_desc(mode, m, layers, *, stream=None, stream_cols=0, head_w=None, head_b=None, head_out=None):
+  """Descriptor of one layer-chained launch (include/mnrf.h mnrf_chain_desc).  layers: list of dicts with
+  w [256, ldw] bf16, optional bias / maskbits / colsum / out, n_stream, stream_col0, stream_kb0, n_res, res_kb0.
+  The tensors must outlive the descriptor (the caller keeps them: level-state / weight buffers)."""
+  d = L.ChainDesc()
+  d.mode, d.num_layers, d.width, d.stream_cols, d.m = mode, len(layers), 256, stream_cols, m
+  if stream is not None:
+    assert stream.dtype == torch.bfloat16 and stream.stride(1) == 1
+    d.stream, d.ldstream = stream.data_ptr(), stream.stride(0)
+  if head_w is not None:
+    d.head_w, d.head_out = head_w.data_ptr(), head_out.data_ptr()
+    d.head_b = head_b.data_ptr() if head_b is not None else None
+  flops = 0.0
+  for j, ly in enumerate(layers):
+    c = d.layer[j]
+    w = ly['w']
+    assert w.dtype == torch.bfloat16 and w.stride(1) == 1
+    c.w, c.ldw = w.data_ptr(), w.stride(0)
+    for name in ('bias', 'colsum'):
+      t = ly.get(name)
+      setattr(c, name, t.data_ptr() if t is not None else None)
+    mb = ly.get('maskbits')
+    if mb is not None:
+      assert mb.dtype == torch.int32 and mb.stride(1) == 1
+      c.maskbits, c.ldmaskbits = mb.data_ptr(), mb.stride(0)
+    out = ly.get('out')
+    if out is not None:
+      assert out.dtype == torch.bfloat16 and out.stride(1) == 1
+      c.out, c.ldo = out.data_ptr(), out.stride(0)
+    c.n_stream, c.stream_col0, c.stream_kb0 = ly.get('n_stream', 0), ly.get('stream_col0', 0), ly.get('stream_kb0', 0)
+    c.n_res, c.res_kb0 = ly.get('n_res', 0), ly.get('res_kb0', 0)
+    flops += 2.0 * m * 256 * 64 * (c.n_stream + c.n_res)
+  return d, flops
+
+
+def mlp_chain(desc):
+  """One launch for a whole 256-wide trunk (forward) or its input-gradient chain (backward)."""
+  lib = L.load()
+  d, flops = desc
+  _count()
+  ev = None
+  if GEMM_EVENTS is not None:
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[0].record()
+  L.check(lib.mnrf_mlp_chain(C.byref(d), L.stream_ptr()))
+  if ev is not None:
+    ev[1].record()
+    GEMM_EVENTS.append((ev[0], ev[1], flops))
+
+
 def head_fwd(x, w_nk, bias, n_out, k, raw=None):
   lib = L.load()
   M = x.shape[0]

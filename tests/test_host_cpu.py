@@ -27,14 +27,15 @@ def test_abi_library_loads_and_exports_header_symbols():
     assert hasattr(l, name)
   # descriptor struct sizes must match the C side (compiled check via a tiny C program)
   import ctypes, subprocess, tempfile
-  src = '#include <stdio.h>\n#include "mnrf.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",sizeof(mnrf_sample_desc),sizeof(mnrf_encode_desc),sizeof(mnrf_gemm_desc),sizeof(mnrf_composite_desc),sizeof(mnrf_loss_desc),sizeof(mnrf_adam_desc),sizeof(mnrf_refdir_desc),sizeof(mnrf_camera_desc),sizeof(mnrf_pack_item));return 0;}'
+  src = '#include <stdio.h>\n#include "mnrf.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",sizeof(mnrf_sample_desc),sizeof(mnrf_encode_desc),sizeof(mnrf_gemm_desc),sizeof(mnrf_composite_desc),sizeof(mnrf_loss_desc),sizeof(mnrf_adam_desc),sizeof(mnrf_refdir_desc),sizeof(mnrf_camera_desc),sizeof(mnrf_pack_item),sizeof(mnrf_chain_layer),sizeof(mnrf_chain_desc));return 0;}'
   with tempfile.TemporaryDirectory() as td:
     open(os.path.join(td, 'a.c'), 'w').write(src)
     subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(td, 'a.c'), '-o', os.path.join(td, 'a')], check=True)
     sizes = list(map(int, subprocess.run([os.path.join(td, 'a')], capture_output=True, text=True).stdout.split()))
   assert sizes == [ctypes.sizeof(lib.SampleDesc), ctypes.sizeof(lib.EncodeDesc), ctypes.sizeof(lib.GemmDesc),
                    ctypes.sizeof(lib.CompositeDesc), ctypes.sizeof(lib.LossDesc), ctypes.sizeof(lib.AdamDesc),
-                   ctypes.sizeof(lib.RefdirDesc), ctypes.sizeof(lib.CameraDesc), ctypes.sizeof(lib.PackItem)]
+                   ctypes.sizeof(lib.RefdirDesc), ctypes.sizeof(lib.CameraDesc), ctypes.sizeof(lib.PackItem),
+                   ctypes.sizeof(lib.ChainLayer), ctypes.sizeof(lib.ChainDesc)]
 
 
 def test_no_cpu_fallback():
