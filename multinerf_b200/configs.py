@@ -66,6 +66,54 @@ class Config:
   apply_bayer_mask: bool = False
   forward_facing: bool = False
   eval_render_interval: int = 1
+  # --- fields used by the callers either side of the hot path (datasets / train / eval / render;
+  #     internal/configs.py:54-172), same names and defaults
+  load_alphabetical: bool = True
+  render_path: bool = False
+  llffhold: int = 8
+  llff_use_all_images_for_training: bool = False
+  use_tiffs: bool = False
+  gc_every: int = 10000
+  vocab_tree_path: Optional[str] = None
+  num_showcase_images: int = 5
+  deterministic_showcase: bool = True
+  vis_decimate: int = 0
+  robustnerf_inlier_quantile: float = 0.5
+  enable_robustnerf_loss: bool = False
+  robustnerf_inner_patch_size: int = 8
+  robustnerf_smoothed_filter_size: int = 3
+  robustnerf_smoothed_inlier_quantile: float = 0.5
+  robustnerf_inner_patch_inlier_quantile: float = 0.5
+  eval_only_once: bool = True
+  eval_save_output: bool = True
+  eval_save_ray_data: bool = False
+  eval_dataset_limit: int = 2 ** 31 - 1
+  eval_quantize_metrics: bool = True
+  eval_crop_borders: int = 0
+  render_video_fps: int = 60
+  render_video_crf: int = 18
+  render_path_frames: int = 120
+  z_variation: float = 0.
+  z_phase: float = 0.
+  render_dist_percentile: float = 0.5
+  render_dist_curve_fn: str = 'log'
+  render_path_file: Optional[str] = None
+  render_job_id: int = 0
+  render_num_jobs: int = 1
+  render_resolution: Optional[Tuple[int, int]] = None
+  render_focal: Optional[float] = None
+  render_camtype: Optional[str] = None
+  render_spherical: bool = False
+  render_save_async: bool = True
+  render_spline_keyframes: Optional[str] = None
+  render_spline_n_interp: int = 30
+  render_spline_degree: int = 5
+  render_spline_smoothness: float = .03
+  render_spline_interpolate_exposure: bool = False
+  exposure_percentile: float = 97.
+  num_border_pixels_to_mask: int = 0
+  autoexpose_renders: bool = False
+  eval_raw_affine_cc: bool = False
 
 
 @dataclasses.dataclass

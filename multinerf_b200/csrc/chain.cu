@@ -29,7 +29,12 @@
 //   warp 0   : TMA producer (one elected lane per CTA)
 //   warp 1   : MMA issuer (leader CTA, one elected lane)
 //   warp 2   : TMEM allocator (512 columns = the two accumulators)
+//   warp 3   : store / hand-off warp: after the epilogue warps have written an activation block it issues the
+//              bulk stores and signals the MMA issuer.  Its cluster-scope release costs a GPU-scope membar in
+//              SASS; keeping that on a warp with no global stores of its own in flight keeps it cheap
+//              (on the epilogue threads it waited for their mask / head stores: 1.36 ms -> see profiles/)
 //   warps 4-11: epilogue (two warps per TMEM lane quadrant, 128 columns each)
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -74,6 +79,8 @@ struct ChainParams {
   const float* head_w;      // FWD: Dense(1) on the last layer's output (density head), fp32 copy of the bf16 row
   const float* head_b;
   float* head_out;
+  int debug;                // MNRF_CHAIN_DEBUG (timing experiments, -DMNRF_TIMING_KNOBS builds only; results are wrong):
+                            // 1 = no epilogue math/smem writes, 2 = no bulk stores, 4 = no mask / head global writes
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -105,7 +112,6 @@ __device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t* bar, uint32_t pa
     }
   }
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // MODE 0: forward  -- epilogue = + bias, ReLU, 1-bit masks out, bf16 activation to smem (+ HBM), density head
 // MODE 1: backward -- epilogue = x ReLU mask (bits in), bias-gradient column sums, bf16 gradient to smem + HBM
@@ -116,13 +122,14 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint8_t* act = smem;                                     // [2][CH_ACT]
   uint8_t* ring = smem + 2 * CH_ACT;                       // [CH_SLOTS][CH_SLOT]
-  float* hpart = reinterpret_cast<float*>(ring + CH_SLOTS * CH_SLOT);      // [128] head partial of column half 1
+  float* hpart = reinterpret_cast<float*>(ring + CH_SLOTS * CH_SLOT);      // [2][128] head partial of column half 1, per block
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(hpart) + 1024);
   uint64_t* full_bar = bars;                               // [CH_SLOTS]  (the leader's are used)
   uint64_t* empty_bar = bars + CH_SLOTS;                   // [CH_SLOTS]
   uint64_t* acc_full = bars + 2 * CH_SLOTS;                // [2] accumulator of block X complete
   uint64_t* act_ready = acc_full + 2;                      // [2] (leader's) epilogue of block X done in both CTAs
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(act_ready + 2);
+  uint64_t* buf_free = act_ready + 2;                      // [2] the bulk store has finished reading block X
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(buf_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,7 +148,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < CH_SLOTS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 2 * CH_EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 2); mbar_init(&buf_free[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2>(tmem_ptr, 512);
@@ -243,13 +250,42 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== store / hand-off warp (both CTAs) =====================
+    for (int64_t unit = pair; unit < p.num_units; unit += num_pairs) {
+      for (int j = 0; j < p.num_layers; ++j) {
+        const ChainLayer& L = p.layer[j];
+        for (int X = 0; X < 2; ++X) {
+          named_bar_sync(1, CH_EPI_THREADS + 32);       // the epilogue warps have written (and fenced) block X
+          if (lane == 0) {
+            bool stored = false;
+            if (L.store
+#ifdef MNRF_TIMING_KNOBS
+                && !(p.debug & 2)
+#endif
+            ) {
+              const int row0 = (int)(unit * CH_UNIT_ROWS + X * 256 + rank * 128);
+              const uint8_t* ablk = act + X * CH_ACT;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) tma_store_2d(&maps.out[j], ablk + k4 * CH_SLOT, k4 * 64, row0);
+              tma_store_commit();
+              stored = true;
+            }
+            mbar_arrive_leader_release(&act_ready[X]);  // accumulator X drained + block X ready, this CTA
+            if (stored) tma_store_wait_read<0>();       // the block may be overwritten once the store has read it
+            mbar_arrive(&buf_free[X]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int ew = warp - 4;
     const int half = ew >> 2;               // column half: [half*128, half*128 + 128)
     const int r_blk = q * 32 + lane;        // row within the CTA's 128-row block
-    const bool issuer = (ew == 0 && lane == 0);
     uint32_t nfull[2] = {0u, 0u};
     float csacc[CH_MAX_LAYERS][4];
 #pragma unroll
@@ -273,11 +309,13 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           mbar_wait(&acc_full[X], nfull[X] & 1u, 4);
           ++nfull[X];
           tc_fence_after();
-          // the bulk store that last read this activation block (two phases ago) must have finished
-          if (issuer) tma_store_wait_read<1>();
-          named_bar_sync(1, CH_EPI_THREADS);
+          // the bulk store that last read this activation block (two phases ago) must have finished reading it
+          mbar_wait(&buf_free[X], (nfull[X] & 1u), 5);      // nfull already counts this phase: parity of the previous one
           uint8_t* ablk = act + X * CH_ACT;
           float hdot = 0.f;
+#ifdef MNRF_TIMING_KNOBS
+          if (!(p.debug & 1))
+#endif
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
             const int c0 = half * 128 + ci * 32;      // first of this pass's 32 columns
@@ -359,23 +397,18 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               *reinterpret_cast<uint4*>(kb + (((chunk0 + g) ^ (r_blk & 7)) << 4)) = o[g];
           }
           tc_fence_before();
-          fence_proxy_async_all();            // generic-proxy writes -> visible to UMMA / TMA (async proxy)
-          if (MODE == 0 && last && p.head_w && half == 1) hpart[r_blk] = hdot;
-          named_bar_sync(1, CH_EPI_THREADS);
-          if (issuer) {
-            if (L.store) {
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) tma_store_2d(&maps.out[j], ablk + k4 * CH_SLOT, k4 * 64, (int)row0);
-            }
-            tma_store_commit();               // one (possibly empty) group per phase keeps wait_group.read<1> exact
-          }
-          mbar_arrive_leader_release(&act_ready[X]);
+          fence_proxy_async();                // generic-proxy writes -> visible to UMMA / TMA (async proxy)
+          if (MODE == 0 && last && p.head_w && half == 1) hpart[X * 128 + r_blk] = hdot;
+          named_bar_sync(1, CH_EPI_THREADS + 32);          // hand the block to warp 3 (stores + signal)
+#ifdef MNRF_TIMING_KNOBS
+          if (p.debug & 4) continue;
+#endif
           if (MODE == 0) {
             if (L.maskbits && row_ok)
               *reinterpret_cast<uint4*>(L.maskbits + row * L.ldmaskbits + half * 4) =
                   make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
             if (last && p.head_w && half == 0 && row_ok)
-              p.head_out[row] = (hdot + hpart[r_blk]) + (p.head_b ? __ldg(p.head_b) : 0.f);
+              p.head_out[row] = (hdot + hpart[X * 128 + r_blk]) + (p.head_b ? __ldg(p.head_b) : 0.f);
           }
         }
       }
@@ -389,7 +422,6 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         }
       }
     }
-    if (issuer) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -456,6 +488,9 @@ extern "C" int mnrf_mlp_chain(const mnrf_chain_desc* d, mnrf_stream stream_) {
     if (make_tmap(&maps.stream, d->stream, d->m, d->stream_cols, d->ldstream, 64, 128)) return 1;
   }
   p.head_w = d->head_w; p.head_b = d->head_b; p.head_out = d->head_out;
+#ifdef MNRF_TIMING_KNOBS
+  p.debug = getenv("MNRF_CHAIN_DEBUG") ? atoi(getenv("MNRF_CHAIN_DEBUG")) : 0;
+#endif
   if (d->head_w) MNRF_CHECK(d->mode == MNRF_CHAIN_FWD && d->head_out && ((uintptr_t)d->head_w % 16) == 0,
                             "mnrf_mlp_chain: the head is a forward output (16-byte aligned weights)");
   const int pairs = (int)std::min<int64_t>(p.num_units, sms / 2);

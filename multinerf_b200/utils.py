@@ -99,3 +99,75 @@ def unshard(x, padding=0):
   if padding > 0:
     y = y[:-padding]
   return y
+
+
+# ---------------------------------------------------------------------------------------------------
+# File / image IO used by the dataset loaders and the eval / render scripts (internal/utils.py:90-171)
+# ---------------------------------------------------------------------------------------------------
+import enum  # noqa: E402
+import os  # noqa: E402
+
+
+class DataSplit(enum.Enum):
+  TRAIN = 'train'
+  TEST = 'test'
+
+
+class BatchingMethod(enum.Enum):
+  """Rays of a batch come from all images or from one image (internal/utils.py:96-99)."""
+  ALL_IMAGES = 'all_images'
+  SINGLE_IMAGE = 'single_image'
+
+
+def open_file(pth, mode='r'):
+  return open(pth, mode=mode)
+
+
+def file_exists(pth):
+  return os.path.exists(pth)
+
+
+def listdir(pth):
+  return os.listdir(pth)
+
+
+def isdir(pth):
+  return os.path.isdir(pth)
+
+
+def makedirs(pth):
+  os.makedirs(pth, exist_ok=True)
+
+
+def load_img(pth):
+  """Image file -> float32 array with the file's own value range (internal/utils.py:134-138)."""
+  from PIL import Image
+  with open(pth, 'rb') as f:
+    return np.array(Image.open(f), dtype=np.float32)
+
+
+def load_exif(pth):
+  """EXIF tags by name, {} when the file has none (internal/utils.py:141-153)."""
+  from PIL import ExifTags, Image
+  with open(pth, 'rb') as f:
+    raw = Image.open(f)._getexif()  # pylint: disable=protected-access
+  return {} if raw is None else {ExifTags.TAGS[k]: v for k, v in raw.items() if k in ExifTags.TAGS}
+
+
+def _to_numpy(x):
+  return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def save_img_u8(img, pth):
+  """[0, 1] image -> 8-bit PNG (NaN -> 0, clipped) (internal/utils.py:156-162)."""
+  from PIL import Image
+  arr = (np.clip(np.nan_to_num(_to_numpy(img)), 0., 1.) * 255.).astype(np.uint8)
+  with open(pth, 'wb') as f:
+    Image.fromarray(arr).save(f, 'PNG')
+
+
+def save_img_f32(depthmap, pth):
+  """Float map (distance, acc) -> float32 TIFF (internal/utils.py:165-168)."""
+  from PIL import Image
+  with open(pth, 'wb') as f:
+    Image.fromarray(np.nan_to_num(_to_numpy(depthmap)).astype(np.float32)).save(f, 'TIFF')

@@ -163,16 +163,16 @@ def test_fullwidth_train_step_vs_oracle(mods, which):
         continue
       rel = float((ka - kb).norm() / kb.norm())
       cos = float((ka @ kb) / (ka.norm() * kb.norm()).clamp(min=1e-30))
-      report[(lname, 'kernel')] = (round(rel, 3), round(cos, 4))
+      report[(mname, lname, 'kernel')] = (round(rel, 3), round(cos, 4))
       ba = torch.tensor(g[mname][lname]['bias']).double().flatten()
       bb = grads_o[(mname, lname, 'bias')].double().flatten()
       if sp.out_dim <= 4:
         # a head's bias gradient is a plain sum of the per-sample gradients: it cancels to (nearly) nothing,
         # so its error is measured against the size of the same head's kernel-gradient entries
         scale = max(float(bb.abs().max()), float(kb.abs().max()))
-        report[(lname, 'bias')] = (round(float((ba - bb).abs().max()) / scale, 3), 1.0)
+        report[(mname, lname, 'bias')] = (round(float((ba - bb).abs().max()) / scale, 3), 1.0)
       else:
-        report[(lname, 'bias')] = (round(float((ba - bb).norm() / bb.norm().clamp(min=1e-12)), 3),
+        report[(mname, lname, 'bias')] = (round(float((ba - bb).norm() / bb.norm().clamp(min=1e-12)), 3),
                                    round(float((ba @ bb) / (ba.norm() * bb.norm()).clamp(min=1e-30)), 4))
   # dY travels between layers in bf16 on both sides with different rounding points, and every ReLU whose
   # pre-activation sits within bf16 noise of zero may flip: the error grows with depth and is largest at
