@@ -29,10 +29,8 @@
 //   warp 0   : TMA producer (one elected lane per CTA)
 //   warp 1   : MMA issuer (leader CTA, one elected lane)
 //   warp 2   : TMEM allocator (512 columns = the two accumulators)
-//   warp 3   : store / hand-off warp: after the epilogue warps have written an activation block it issues the
-//              bulk stores and signals the MMA issuer.  Its cluster-scope release costs a GPU-scope membar in
-//              SASS; keeping that on a warp with no global stores of its own in flight keeps it cheap
-//              (on the epilogue threads it waited for their mask / head stores: 1.36 ms -> see profiles/)
+//   warp 3   : store warp: once the epilogue threads have written an activation block it issues the bulk stores
+//              of that block (TMA) and tells the epilogue when the block may be overwritten
 //   warps 4-11: epilogue (two warps per TMEM lane quadrant, 128 columns each)
 #include <stdlib.h>
 #include <string.h>
@@ -79,40 +77,38 @@ struct ChainParams {
   const float* head_w;      // FWD: Dense(1) on the last layer's output (density head), fp32 copy of the bf16 row
   const float* head_b;
   float* head_out;
+  long long* trace;         // -DMNRF_TIMING_KNOBS + MNRF_CHAIN_TRACE=<device ptr>: clock64 event log of CTA 0
   int debug;                // MNRF_CHAIN_DEBUG (timing experiments, -DMNRF_TIMING_KNOBS builds only; results are wrong):
                             // 1 = no epilogue math/smem writes, 2 = no bulk stores, 4 = no mask / head global writes
 };
 
+// two fp32 -> packed bf16x2 with ReLU in the conversion (one instruction for both lanes)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+#ifdef MNRF_TIMING_KNOBS
+// event log of the leader CTA of pair 0: trace[0] = event count, then (tag, unit*100 + j*10 + X, clock64) triples
+#define CH_TRACE(tag, unit, j, X)                                                              \
+  do {                                                                                          \
+    if (p.trace && blockIdx.x == 0 && (unit) < 3 * (gridDim.x >> 1)) {                          \
+      const unsigned long long n_ = atomicAdd((unsigned long long*)p.trace, 1ull);              \
+      if (n_ < 4000) {                                                                          \
+        p.trace[1 + 3 * n_] = (tag); p.trace[2 + 3 * n_] = (long long)((unit) * 100 + (j) * 10 + (X)); \
+        p.trace[3 + 3 * n_] = clock64();                                                        \
+      }                                                                                         \
+    }                                                                                           \
+  } while (0)
+#else
+#define CH_TRACE(tag, unit, j, X) do {} while (0)
+#endif
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-// cluster-scope release/acquire pair for "activation block ready": the peer CTA's shared-memory writes
-// (made visible to the async proxy with fence.proxy.async) are consumed by MMAs the leader issues.
-__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t* bar, uint32_t parity, int tag) {
-  if (mbar_try_wait_acq_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_acq_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mnrf mlp_chain: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-
 // MODE 0: forward  -- epilogue = + bias, ReLU, 1-bit masks out, bf16 activation to smem (+ HBM), density head
 // MODE 1: backward -- epilogue = x ReLU mask (bits in), bias-gradient column sums, bf16 gradient to smem + HBM
 template <int MODE>
@@ -129,7 +125,8 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   uint64_t* acc_full = bars + 2 * CH_SLOTS;                // [2] accumulator of block X complete
   uint64_t* act_ready = acc_full + 2;                      // [2] (leader's) epilogue of block X done in both CTAs
   uint64_t* buf_free = act_ready + 2;                      // [2] the bulk store has finished reading block X
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(buf_free + 2);
+  uint64_t* blk_written = buf_free + 2;                    // [2] all epilogue threads of this CTA have written block X
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(blk_written + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,7 +145,12 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < CH_SLOTS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 2); mbar_init(&buf_free[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&act_ready[i], 2 * CH_EPI_THREADS);
+      mbar_init(&buf_free[i], 1);
+      mbar_init(&blk_written[i], CH_EPI_THREADS);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2>(tmem_ptr, 512);
@@ -168,6 +170,17 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         if (++slot == CH_SLOTS) { slot = 0; phase ^= 1; }
       };
       for (int64_t unit = pair; unit < p.num_units; unit += num_pairs) {
+        // The streamed operand comes from HBM: with three k-blocks in flight (1.5k cycles of MMA work) a cold
+        // DRAM access (~3k cycles) would stall the first layer, so the NEXT unit's tiles are pulled into L2 now.
+        if (unit + num_pairs < p.num_units) {
+          for (int j = 0; j < p.num_layers; ++j) {
+            const ChainLayer& L = p.layer[j];
+            for (int X = 0; X < 2; ++X) {
+              const int prow = (int)((unit + num_pairs) * CH_UNIT_ROWS + X * 256 + rank * 128);
+              for (int s2 = 0; s2 < L.n_stream; ++s2) tma_prefetch_2d(&maps.stream, L.stream_col0 + s2 * 64, prow);
+            }
+          }
+        }
         for (int j = 0; j < p.num_layers; ++j) {
           const ChainLayer& L = p.layer[j];
           for (int X = 0; X < 2; ++X) {
@@ -200,9 +213,11 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           const ChainLayer& L = p.layer[j];
           for (int X = 0; X < 2; ++X) {
             // accumulator X drained and (for resident operands) activation block X written, in both CTAs
-            mbar_wait_acq_cluster(&act_ready[X], (nready[X] & 1u) ^ 1u, 2);
+            CH_TRACE(10, unit, j, X);
+            mbar_wait(&act_ready[X], (nready[X] & 1u) ^ 1u, 2);
             ++nready[X];
             tc_fence_after();
+            CH_TRACE(11, unit, j, X);
             const uint32_t tmem_d = tmem_base + (uint32_t)X * CH_W;
             uint32_t accumulate = 0u;
             auto mma_kblock = [&](uint32_t a_addr, uint32_t b_addr) {
@@ -246,19 +261,25 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             };
             if (X == 0) { stream_part(); res_part(); } else { res_part(); stream_part(); }
             umma_commit<2>(&acc_full[X]);
+            CH_TRACE(12, unit, j, X);
           }
         }
       }
     }
   } else if (warp == 3) {
-    // ===================== store / hand-off warp (both CTAs) =====================
-    for (int64_t unit = pair; unit < p.num_units; unit += num_pairs) {
-      for (int j = 0; j < p.num_layers; ++j) {
-        const ChainLayer& L = p.layer[j];
-        for (int X = 0; X < 2; ++X) {
-          named_bar_sync(1, CH_EPI_THREADS + 32);       // the epilogue warps have written (and fenced) block X
-          if (lane == 0) {
-            bool stored = false;
+    // ===================== store warp (both CTAs) =====================
+    // Waits until all epilogue threads of this CTA have written (and fenced) an activation block, issues its bulk
+    // stores and tells the epilogue when the block may be overwritten.  (The MMA issuer is signalled by the
+    // epilogue threads themselves, so the stores are off the critical path.)
+    if (lane == 0) {
+      uint32_t nwritten[2] = {0u, 0u};
+      for (int64_t unit = pair; unit < p.num_units; unit += num_pairs) {
+        for (int j = 0; j < p.num_layers; ++j) {
+          const ChainLayer& L = p.layer[j];
+          for (int X = 0; X < 2; ++X) {
+            mbar_wait(&blk_written[X], nwritten[X] & 1u, 6);
+            ++nwritten[X];
+            CH_TRACE(30, unit, j, X);
             if (L.store
 #ifdef MNRF_TIMING_KNOBS
                 && !(p.debug & 2)
@@ -269,23 +290,28 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) tma_store_2d(&maps.out[j], ablk + k4 * CH_SLOT, k4 * 64, row0);
               tma_store_commit();
-              stored = true;
+              tma_store_wait_read<0>();                 // the block may be overwritten once the store has read it
             }
-            mbar_arrive_leader_release(&act_ready[X]);  // accumulator X drained + block X ready, this CTA
-            if (stored) tma_store_wait_read<0>();       // the block may be overwritten once the store has read it
             mbar_arrive(&buf_free[X]);
+            CH_TRACE(32, unit, j, X);
           }
-          __syncwarp();
         }
       }
+      tma_store_wait_all();
     }
-    if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int ew = warp - 4;
     const int half = ew >> 2;               // column half: [half*128, half*128 + 128)
     const int r_blk = q * 32 + lane;        // row within the CTA's 128-row block
+    // shared-space addresses of this thread's row in the two activation blocks, and the eight swizzled 16-byte
+    // chunk offsets of a 128-byte row (SWIZZLE_128B: chunk index XOR (row & 7))
+    const uint32_t row_s = smem_u32(act) + (uint32_t)r_blk * 128u;
+    uint32_t swz[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) swz[c] = (uint32_t)((c ^ (r_blk & 7)) << 4);
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
     uint32_t nfull[2] = {0u, 0u};
     float csacc[CH_MAX_LAYERS][4];
 #pragma unroll
@@ -297,6 +323,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       for (int j = 0; j < p.num_layers; ++j) {
         const ChainLayer& L = p.layer[j];
         const bool last = (j == p.num_layers - 1);
+        const bool do_head = (MODE == 0) && last && p.head_w != nullptr;
         for (int X = 0; X < 2; ++X) {
           const int64_t row0 = unit * CH_UNIT_ROWS + X * 256 + rank * 128;
           const int64_t row = row0 + r_blk;
@@ -306,12 +333,14 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             const uint4 t = *reinterpret_cast<const uint4*>(L.maskbits + row * L.ldmaskbits + half * 4);
             mbits[0] = t.x; mbits[1] = t.y; mbits[2] = t.z; mbits[3] = t.w;
           }
+          if (ew == 0 && lane == 0) CH_TRACE(20, unit, j, X);
           mbar_wait(&acc_full[X], nfull[X] & 1u, 4);
           ++nfull[X];
           tc_fence_after();
+          if (ew == 0 && lane == 0) CH_TRACE(21, unit, j, X);
           // the bulk store that last read this activation block (two phases ago) must have finished reading it
           mbar_wait(&buf_free[X], (nfull[X] & 1u), 5);      // nfull already counts this phase: parity of the previous one
-          uint8_t* ablk = act + X * CH_ACT;
+          const uint32_t blk_s = row_s + (uint32_t)(X * CH_ACT + half * 2 * CH_SLOT);
           float hdot = 0.f;
 #ifdef MNRF_TIMING_KNOBS
           if (!(p.debug & 1))
@@ -320,86 +349,79 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int ci = 0; ci < 4; ++ci) {
             const int c0 = half * 128 + ci * 32;      // first of this pass's 32 columns
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(X * CH_W + c0), r);
-            float4 cvec[8];
-            if (MODE == 0 && L.bias) {
-              const float4* cp = reinterpret_cast<const float4*>(L.bias + c0);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) cvec[t] = __ldg(cp + t);
-            }
+            tmem_ld32(taddr_row + (uint32_t)(X * CH_W + ci * 32), r);
             tmem_ld_wait();
             float v[32];
 #pragma unroll
             for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
+            uint32_t o[16];
             if (MODE == 0) {
-              if (L.bias) {
+              const float4* cp = reinterpret_cast<const float4*>(L.bias + c0);
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  v[4 * t] += cvec[t].x; v[4 * t + 1] += cvec[t].y; v[4 * t + 2] += cvec[t].z; v[4 * t + 3] += cvec[t].w;
-                }
+              for (int t = 0; t < 8; ++t) {
+                const float4 bv = __ldg(cp + t);
+                v[4 * t] += bv.x; v[4 * t + 1] += bv.y; v[4 * t + 2] += bv.z; v[4 * t + 3] += bv.w;
               }
+              // ReLU is folded into the bf16 conversion (cvt.rn.relu); the mask is the sign of the fp32
+              // pre-activation (v > 0  <=>  stored activation > 0: bf16 keeps fp32's exponent range)
               uint32_t bits = 0u;
 #pragma unroll
-              for (int t = 0; t < 32; ++t) {
-                v[t] = fmaxf(v[t], 0.f);
-                bits |= (v[t] > 0.f ? 1u : 0u) << t;
-              }
+              for (int t = 0; t < 32; ++t) bits |= (v[t] > 0.f ? 1u : 0u) << t;
               mbits[ci] = bits;
+#pragma unroll
+              for (int t = 0; t < 16; ++t) o[t] = pack_bf16_relu(v[2 * t], v[2 * t + 1]);
+              if (do_head) {
+                // Dense(1) on the bf16-rounded activation, fp32 accumulate (what the head kernel computes)
+                const float4* hw = reinterpret_cast<const float4*>(p.head_w + c0);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  const float4 h = __ldg(hw + t);
+                  hdot += bf16_lo(o[2 * t]) * h.x + bf16_hi(o[2 * t]) * h.y + bf16_lo(o[2 * t + 1]) * h.z +
+                          bf16_hi(o[2 * t + 1]) * h.w;
+                }
+              }
             } else {
               if (L.maskbits) {
                 const uint32_t bits = mbits[ci];
 #pragma unroll
                 for (int t = 0; t < 32; ++t) v[t] = (bits >> t) & 1u ? v[t] : 0.f;
               }
-            }
-            uint4 o[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              o[g].x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-              o[g].y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-              o[g].z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-              o[g].w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-            }
-            if (MODE == 1 && L.colsum) {
-              // column sums over this warp's 32 rows, in place on v (already packed): shuffle transpose-reduce,
-              // lane t ends with column t; rows past M hold zeros (zero-filled operand, zero mask)
+              for (int t = 0; t < 16; ++t) o[t] = pack_bf16(v[2 * t], v[2 * t + 1]);
+              if (L.colsum) {
+                // column sums over this warp's 32 rows, in place on v (already packed): shuffle transpose-reduce,
+                // lane t ends with column t; rows past M hold zeros (zero-filled operand, zero mask)
 #pragma unroll
-              for (int sh = 16, n = 32; sh >= 1; sh >>= 1, n >>= 1) {
-                const bool up = (lane & sh) != 0;
+                for (int sh = 16, n = 32; sh >= 1; sh >>= 1, n >>= 1) {
+                  const bool up = (lane & sh) != 0;
 #pragma unroll
-                for (int i = 0; i < n / 2; ++i) {
-                  const float send = up ? v[i] : v[i + n / 2];
-                  const float keep = up ? v[i + n / 2] : v[i];
-                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sh);
+                  for (int i = 0; i < n / 2; ++i) {
+                    const float send = up ? v[i] : v[i + n / 2];
+                    const float keep = up ? v[i + n / 2] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sh);
+                  }
                 }
-              }
 #pragma unroll
-              for (int jj = 0; jj < CH_MAX_LAYERS; ++jj)
-                if (jj == j) csacc[jj][ci] += v[0];
-            }
-            if (MODE == 0 && last && p.head_w) {
-              // Dense(1) on the bf16-rounded activation, fp32 accumulate (what the head kernel computes)
-              const float4* hw = reinterpret_cast<const float4*>(p.head_w + c0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint32_t w4[4] = {o[g].x, o[g].y, o[g].z, o[g].w};
-                const float4 h0 = __ldg(hw + 2 * g), h1 = __ldg(hw + 2 * g + 1);
-                hdot += bf16_lo(w4[0]) * h0.x + bf16_hi(w4[0]) * h0.y + bf16_lo(w4[1]) * h0.z + bf16_hi(w4[1]) * h0.w;
-                hdot += bf16_lo(w4[2]) * h1.x + bf16_hi(w4[2]) * h1.y + bf16_lo(w4[3]) * h1.z + bf16_hi(w4[3]) * h1.w;
+                for (int jj = 0; jj < CH_MAX_LAYERS; ++jj)
+                  if (jj == j) csacc[jj][ci] += v[0];
               }
             }
-            // K-major SWIZZLE_128B k-block (the layout TMA produces and UMMA / the bulk store consume):
-            // row pitch 128 B, 16-byte chunk index XOR (row & 7)
-            uint8_t* kb = ablk + (c0 >> 6) * CH_SLOT + r_blk * 128;
-            const int chunk0 = (ci & 1) * 4;
+            // K-major SWIZZLE_128B k-block (the layout TMA produces and UMMA / the bulk store consume)
+            const uint32_t kb_s = blk_s + (uint32_t)((ci >> 1) * CH_SLOT);
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(kb + (((chunk0 + g) ^ (r_blk & 7)) << 4)) = o[g];
+              st_shared_v4(kb_s + swz[(ci & 1) * 4 + g], o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
           }
+          if (ew == 0 && lane == 0) CH_TRACE(23, unit, j, X);
           tc_fence_before();
           fence_proxy_async();                // generic-proxy writes -> visible to UMMA / TMA (async proxy)
-          if (MODE == 0 && last && p.head_w && half == 1) hpart[X * 128 + r_blk] = hdot;
-          named_bar_sync(1, CH_EPI_THREADS + 32);          // hand the block to warp 3 (stores + signal)
+          // accumulator X drained + this thread's part of block X written: signal the MMA issuer (leader CTA) and
+          // the store warp.  Plain (CTA-scope) arrives: no DATA crosses SMs here -- each CTA's tensor core reads
+          // its own rows of the A operand from its own shared memory -- so a cluster-scope release (MEMBAR.ALL.GPU
+          // in SASS) is not needed.
+          mbar_arrive_leader(&act_ready[X]);
+          mbar_arrive(&blk_written[X]);
+          if (ew == 0 && lane == 0) CH_TRACE(25, unit, j, X);
 #ifdef MNRF_TIMING_KNOBS
           if (p.debug & 4) continue;
 #endif
@@ -407,8 +429,14 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             if (L.maskbits && row_ok)
               *reinterpret_cast<uint4*>(L.maskbits + row * L.ldmaskbits + half * 4) =
                   make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-            if (last && p.head_w && half == 0 && row_ok)
-              p.head_out[row] = (hdot + hpart[X * 128 + r_blk]) + (p.head_b ? __ldg(p.head_b) : 0.f);
+            if (do_head) {
+              // the two column halves of a row meet in shared memory (warps of one half only sync among the
+              // 256 epilogue threads here, once per unit and block -- off the MMA's critical path)
+              if (half == 1) hpart[X * 128 + r_blk] = hdot;
+              named_bar_sync(1, CH_EPI_THREADS);
+              if (half == 0 && row_ok)
+                p.head_out[row] = (hdot + hpart[X * 128 + r_blk]) + (p.head_b ? __ldg(p.head_b) : 0.f);
+            }
           }
         }
       }
@@ -490,6 +518,7 @@ extern "C" int mnrf_mlp_chain(const mnrf_chain_desc* d, mnrf_stream stream_) {
   p.head_w = d->head_w; p.head_b = d->head_b; p.head_out = d->head_out;
 #ifdef MNRF_TIMING_KNOBS
   p.debug = getenv("MNRF_CHAIN_DEBUG") ? atoi(getenv("MNRF_CHAIN_DEBUG")) : 0;
+  p.trace = getenv("MNRF_CHAIN_TRACE") ? reinterpret_cast<long long*>(strtoull(getenv("MNRF_CHAIN_TRACE"), nullptr, 0)) : nullptr;
 #endif
   if (d->head_w) MNRF_CHECK(d->mode == MNRF_CHAIN_FWD && d->head_out && ((uintptr_t)d->head_w % 16) == 0,
                             "mnrf_mlp_chain: the head is a forward output (16-byte aligned weights)");

@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmnrf_b200.so')
+# MNRF_LIB: an alternative build of the same library (kernel timing experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get('MNRF_LIB') or os.path.join(_HERE, 'libmnrf_b200.so')
 
 
 class MnrfError(RuntimeError):

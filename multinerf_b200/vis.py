@@ -20,7 +20,9 @@ def weighted_percentile(x, w, ps, assume_sorted=False):
   x, w = np.reshape(x, [-1]), np.reshape(w, [-1])
   if not assume_sorted:
     order = np.argsort(x)
-    x, w = x[order], w[order]
+    # the depth triplet passes a 3-channel value with a 1-channel weight: jnp's gather clamps the
+    # out-of-range indices (vis.py:27-28), which is mirrored here
+    x, w = x[order], w[np.minimum(order, w.shape[0] - 1)]
   acc_w = np.cumsum(w)
   return np.interp(np.array(ps) * (acc_w[-1] / 100), acc_w, x)
 
