@@ -108,7 +108,9 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
   G = {'state': 0, 'fb': None, 'opt': None, 'rays': None, 'target': None, 'jitter': None,
        'noise': None, 'launches': 0}
   import os
-  GRAPH_NCCL = os.environ.get('MNRF_GRAPH_NCCL', '1') != '0'
+  # capturing the NCCL all-reduce inside the step graph hangs on this stack (torch 2.11 / NCCL 2.28, measured on
+  # 2 x B200 in round 2): opt-in only
+  GRAPH_NCCL = os.environ.get('MNRF_GRAPH_NCCL', '0') == '1'
 
   # Backward runs the levels last to first, so a module's gradient is final once the lowest level that
   # uses it is done: for 360.gin the NerfMLP segment (34.7 of 36 MB) is final after level 2 and its
@@ -122,9 +124,9 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       first_use.setdefault(mname, i)
     return {i: mname for mname, i in first_use.items() if i > 0}
 
-  def fwd_bwd(rng, rays, target, train_frac, anneal_ptr, world=1):
+  def fb_begin(rng, rays, target, train_frac, anneal_ptr):
+    """Zero the gradients, run the forward pass of every level; returns the context of the backward pass."""
     params = model.params
-    stats_buf = stats_view(params)
     lossmult = rays.lossmult
     if config.disable_multiscale_loss:
       lossmult = torch.ones_like(lossmult)
@@ -134,49 +136,71 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     states = model.forward_levels(rng if config.randomized else None, rays, train_frac,
                                   compute_extras=False, want_samples=False, impl=impl,
                                   anneal_dev=anneal_ptr, loss_config=config, zero_glo=False)
-    fine = states[-1]
-    n = len(states)
-    early = early_segments(n) if world > 1 else {}
-    pending, reduced = [], []
+    return dict(params=params, states=states, rays=rays, target=target, lossmult=lossmult, inv_denom=inv_denom,
+                stats=stats_view(params))
+
+  def fb_level(ctx, i):
+    """Losses + backward of level i (accumulates parameter gradients)."""
+    params, states, rays = ctx['params'], ctx['states'], ctx['rays']
+    st, fine, n = states[i], states[-1], len(states)
+    is_fine = i == n - 1
+    ops.composite_bwd(
+        st.raw_density, st.raw_rgb, st.sdist, rays.directions, rays.near_flat, rays.far_flat,
+        ctx['target'], ctx['lossmult'], ctx['inv_denom'], ctx['stats'][i], cfg=st.comp_cfg,
+        loss_type=config.data_loss_type, charb_padding=config.charb_padding,
+        data_mult=config.data_loss_mult if is_fine else config.data_coarse_loss_mult,
+        distortion_mult=config.distortion_loss_mult if is_fine else 0.0,
+        interlevel_mult=0.0 if is_fine else config.interlevel_loss_mult,
+        sdist_fine=None if is_fine else fine.sdist,
+        weights_fine=None if is_fine else fine.comp['weights'],
+        density_noise=st.noise, bg_rgb=st.bg_rgb, rgb_scale=st.rgb_scale, d_raw_density=st.d_raw_density,
+        d_raw_rgb=st.d_raw_rgb, d_rgb_scale=_d_scale_buf(st),
+        raw_diffuse=st.heads.get('diffuse'), raw_tint=st.heads.get('tint'),
+        extra_dw=st.extra_dw if st.loss_mults is not None else None,
+        d_raw_diffuse=st.d_heads.get('diffuse'), d_raw_tint=st.d_heads.get('tint'))
+    if st.rgb_scale is not None and mcfg.learned_exposure_scaling:
+      # d offsets[idx] += [idx > 0] * exposure_values * d_scale   (adjoint of models.py:262-267)
+      eidx = rays.exposure_idx[:, 0].long()
+      g = (eidx > 0).to(torch.float32)[:, None] * rays.exposure_values * st.d_rgb_scale
+      params.seg('exposure_scaling_offsets', params.grads).view(-1, 3).index_add_(0, eidx, g)
+    model._mlp_backward(st, model.mlps[st.mname], rays=rays, impl=impl, loss_mults=st.loss_mults,
+                        stats=ctx['stats'][i])
+
+  def split_level(n_levels, world):
+    """Level after whose backward the first gradient segment is final (None: exchange everything at the end)."""
+    early = early_segments(n_levels) if world > 1 else {}
+    return (max(early), early[max(early)]) if early else (None, None)
+
+  def exchange_early(params, mname):
+    o, cnt = params.offsets[mname]
+    return dist.all_reduce(params.grads_ext[o:o + cnt], op=dist.ReduceOp.SUM, async_op=True), (o, o + cnt)
+
+  def exchange_rest(params, done, pending):
+    """Everything not yet exchanged (contiguous ranges of the flat buffer, statistics tail included)."""
+    pos = 0
+    for lo, hi in sorted(done) + [(params.grads_ext.numel(), params.grads_ext.numel())]:
+      if lo > pos:
+        dist.all_reduce(params.grads_ext[pos:lo], op=dist.ReduceOp.SUM)
+      pos = hi
+    for w in pending:
+      w.wait()
+
+  def fwd_bwd(rng, rays, target, train_frac, anneal_ptr, world=1):
+    """Eager step body: forward, backward last level to first, gradient exchange (world > 1)."""
+    ctx = fb_begin(rng, rays, target, train_frac, anneal_ptr)
+    n = len(ctx['states'])
+    split, seg = split_level(n, world)
+    pending, done = [], []
     for i in range(n - 1, -1, -1):
-      st = states[i]
-      is_fine = i == n - 1
-      ops.composite_bwd(
-          st.raw_density, st.raw_rgb, st.sdist, rays.directions, rays.near_flat, rays.far_flat,
-          target, lossmult, inv_denom, stats_buf[i], cfg=st.comp_cfg,
-          loss_type=config.data_loss_type, charb_padding=config.charb_padding,
-          data_mult=config.data_loss_mult if is_fine else config.data_coarse_loss_mult,
-          distortion_mult=config.distortion_loss_mult if is_fine else 0.0,
-          interlevel_mult=0.0 if is_fine else config.interlevel_loss_mult,
-          sdist_fine=None if is_fine else fine.sdist,
-          weights_fine=None if is_fine else fine.comp['weights'],
-          density_noise=st.noise, bg_rgb=st.bg_rgb, rgb_scale=st.rgb_scale, d_raw_density=st.d_raw_density,
-          d_raw_rgb=st.d_raw_rgb, d_rgb_scale=_d_scale_buf(st),
-          raw_diffuse=st.heads.get('diffuse'), raw_tint=st.heads.get('tint'),
-          extra_dw=st.extra_dw if st.loss_mults is not None else None,
-          d_raw_diffuse=st.d_heads.get('diffuse'), d_raw_tint=st.d_heads.get('tint'))
-      if st.rgb_scale is not None and mcfg.learned_exposure_scaling:
-        # d offsets[idx] += [idx > 0] * exposure_values * d_scale   (adjoint of models.py:262-267)
-        eidx = rays.exposure_idx[:, 0].long()
-        g = (eidx > 0).to(torch.float32)[:, None] * rays.exposure_values * st.d_rgb_scale
-        params.seg('exposure_scaling_offsets', params.grads).view(-1, 3).index_add_(0, eidx, g)
-      model._mlp_backward(st, model.mlps[st.mname], rays=rays, impl=impl, loss_mults=st.loss_mults,
-                          stats=stats_buf[i])
-      if i in early:
-        o, cnt = params.offsets[early[i]]
-        pending.append(dist.all_reduce(params.grads_ext[o:o + cnt], op=dist.ReduceOp.SUM, async_op=True))
-        reduced.append((o, o + cnt))
+      fb_level(ctx, i)
+      if i == split:
+        w, rng_ = exchange_early(ctx['params'], seg)
+        pending.append(w)
+        done.append(rng_)
     if decay_views:
       weight_decay()
     if world > 1:
-      # everything not yet exchanged (contiguous ranges of the flat buffer, stats tail included)
-      pos = 0
-      for lo, hi in sorted(reduced) + [(params.grads_ext.numel(), params.grads_ext.numel())]:
-        if lo > pos:
-          dist.all_reduce(params.grads_ext[pos:lo], op=dist.ReduceOp.SUM)
-        pos = hi
-      for w in pending:
-        w.wait()
+      exchange_rest(ctx['params'], done, pending)
 
   def weight_decay():
     # loss += mult * sum(w^2)  ->  grad += 2 mult w ; the loss value goes to stats row 0, slot 6
@@ -293,18 +317,33 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       G['target'] = target.clone()
       torch.cuda.synchronize()
       before = ops.LAUNCHES
+      n_lv = len(sched)
+      split, seg = split_level(n_lv, world)
+      G['split'] = None
       if world > 1 and not GRAPH_NCCL:
-        # two graphs around eager NCCL calls
+        # NCCL stays outside the graphs (capturing it hung on this stack, round 2): the step is two graphs around
+        # the exchange, or THREE when a gradient segment is final early -- [forward + backward down to the split
+        # level] | async all-reduce of that segment | [remaining backward levels] | all-reduce of the rest |
+        # [clip + Adam + repack] -- so the big NerfMLP exchange overlaps the PropMLP backward
         G['fb'] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(G['fb']):
-          fwd_bwd(rand, G['rays'], G['target'], train_frac, anneal_dev, 1)
+          ctx = fb_begin(rand, G['rays'], G['target'], train_frac, anneal_dev)
+          for i in range(n_lv - 1, (split if split is not None else 0) - 1, -1):
+            fb_level(ctx, i)
+          if split is None and decay_views:
+            weight_decay()
+        if split is not None:
+          G['split'] = seg
+          G['fb2'] = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(G['fb2'], pool=G['fb'].pool()):
+            for i in range(split - 1, -1, -1):
+              fb_level(ctx, i)
         G['opt'] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(G['opt']):
           optim(grad_scale, params.step, lr, dyn)
       else:
-        # ONE graph for the whole step: forward, backward, the gradient all-reduce(s) (NCCL kernels are
-        # captured on their own stream, so the NerfMLP exchange overlaps the PropMLP backward as a parallel
-        # branch of the graph), clip + Adam + weight repack
+        # ONE graph for the whole step: forward, backward, (world > 1: the gradient all-reduces, captured on
+        # NCCL's stream as parallel branches), clip + Adam + weight repack
         G['fb'] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(G['fb']):
           fwd_bwd(rand, G['rays'], G['target'], train_frac, anneal_dev, world)
@@ -323,7 +362,12 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       G['target'].copy_(target, non_blocking=True)
     G['fb'].replay()
     if G['opt'] is not None:
-      allreduce_flat_(params, world)
+      if G['split'] is not None:
+        w, rng_ = exchange_early(params, G['split'])
+        G['fb2'].replay()
+        exchange_rest(params, [rng_], [w])
+      else:
+        allreduce_flat_(params, world)
       G['opt'].replay()
     ops.LAUNCHES += G['launches']
     return state, LazyStats(stats_view(params).clone(), n, grad_scale), rng
