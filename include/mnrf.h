@@ -155,6 +155,16 @@ int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, c
               const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
               float* colsum, const mnrf_bf16* addend, void* out, mnrf_stream stream);
 
+/* Weight gradient with side sums computed from the operand tiles the main loop stages (the epilogue warps
+ * are idle there), so the bias gradient and the gradient of a Dense(1) head on the same activation cost no
+ * extra pass over HBM:
+ *   out[Mo,N] += A[R,Mo]^T B[R,N]                       (as mnrf_gemm, mode MNRF_GEMM_WGRAD; A = X, B = dY)
+ *   bsum[N]   += sum_r B[r, :]                          (optional: bias gradient of the layer)
+ *   side_aw[Mo] += sum_r side_w[r] * A[r, :]            (optional: dW of a Dense(1) head reading X, with
+ *                                                        side_w = its d(raw output), models.py:460) */
+int mnrf_gemm_wgrad(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, float* bsum,
+                    const float* side_w, float* side_aw, float* out, mnrf_stream stream);
+
 /* ---- layer-chained 256-wide MLP trunk ------------------------------------------------------
  * ONE persistent launch walks 512-row units of samples through all Dense layers of a 256-wide trunk
  * (forward; models.py:441-465 incl. the skip concat) or through its whole input-gradient chain

@@ -8,7 +8,8 @@ namespace mnrf {
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                    const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                   float* colsum, const mnrf_bf16* addend, void* out, cudaStream_t stream);
+                   float* colsum, const mnrf_bf16* addend, float* side_bsum, const float* side_w, float* side_aw,
+                   void* out, cudaStream_t stream);
 
 __device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
@@ -88,7 +89,7 @@ extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf
   cudaStream_t s = (cudaStream_t)stream;
   if (colsum) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD, "mnrf_gemm: colsum is a DGRAD output");
   if (addend) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD, "mnrf_gemm: addend is a DGRAD input");
-  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, maskbits, colsum, addend, out, s);
+  if (d->impl == 0) return gemm_tc_launch(d, a, b, bias, rowv, colv, mask, maskbits, colsum, addend, nullptr, nullptr, nullptr, out, s);
   dim3 block(16, 16);
   if (d->mode != MNRF_GEMM_WGRAD) {
     dim3 grid((d->n + 15) / 16, (unsigned)((d->m + 15) / 16));
@@ -115,5 +116,25 @@ extern "C" int mnrf_gemm(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf
                                                reinterpret_cast<float*>(out), rpb);
   }
   MNRF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mnrf_gemm_wgrad(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, float* bsum,
+                               const float* side_w, float* side_aw, float* out, mnrf_stream stream) {
+  using namespace mnrf;
+  if (d && (d->m == 0 || d->n == 0 || d->k == 0)) return 0;
+  MNRF_CHECK(d && a && b && out, "mnrf_gemm_wgrad: null pointer");
+  MNRF_CHECK(d->mode == MNRF_GEMM_WGRAD, "mnrf_gemm_wgrad: mode must be MNRF_GEMM_WGRAD");
+  MNRF_CHECK((side_w == nullptr) == (side_aw == nullptr), "mnrf_gemm_wgrad: side_w and side_aw come together");
+  if (d->impl == 0)
+    return gemm_tc_launch(d, a, b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bsum, side_w, side_aw,
+                          out, (cudaStream_t)stream);
+  // SIMT reference: the plain weight gradient, then the side sums as separate passes
+  if (int rc = mnrf_gemm(d, a, b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out, stream)) return rc;
+  if (bsum)
+    if (int rc = mnrf_colsum(d->k, d->n, b, d->ldb, bsum, stream)) return rc;
+  if (side_aw)      // side_aw[m] += sum_r side_w[r] * A[r, m]  ==  the dW of a Dense(1) head on A with draw = side_w
+    if (int rc = mnrf_head_bwd(d->k, (int32_t)d->m, 1, a, d->lda, a, side_w, nullptr, 0, 0, side_aw, nullptr, nullptr, stream))
+      return rc;
   return 0;
 }

@@ -70,6 +70,10 @@ struct GemmParams {
   int debug;                  // MNRF_GEMM_DEBUG (timing experiments only): 1 = skip the epilogue, 2 = skip stores
   float* colsum;              // DGRAD: colsum[N] += column sums of the output (bias gradient of the
                               // layer that produced the masking activation), from the epilogue registers
+  // WGRAD side sums, computed by the (otherwise idle) epilogue warps from the operand tiles the main loop stages:
+  float* side_bsum;           //   side_bsum[n] += sum_r B[r, n]            (bias gradient: column sums of dY)
+  const float* side_w;        //   side_aw[m]  += sum_r side_w[r] * A[r, m] (weight gradient of a Dense(1) head
+  float* side_aw;             //                                             that reads the same activation X)
   void* out;
 };
 
@@ -88,7 +92,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* empty_bar = bars + NUM_STAGES;         // [NUM_STAGES]
   uint64_t* tfull_bar = bars + 2 * NUM_STAGES;     // [NUM_ACC]
   uint64_t* tempty_bar = tfull_bar + NUM_ACC;      // [NUM_ACC]     (CTAS=2: the leader's are used)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + NUM_ACC);
+  uint64_t* mdone_bar = tempty_bar + NUM_ACC;      // [NUM_STAGES]  WGRAD side sums: the MMAs of this stage have retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mdone_bar + NUM_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,6 +103,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_m_units = p.num_m_blocks / CTAS;               // 128*CTAS-row units
   const int total_tiles = num_m_units * p.num_n_blocks * p.num_splits;
   constexpr bool kWgrad = (MODE == MNRF_GEMM_WGRAD);
+  // WGRAD side sums: the epilogue warps also consume every operand stage, after the MMAs that read it
+  const bool side = kWgrad && (p.side_bsum != nullptr || p.side_aw != nullptr);
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a);
@@ -105,7 +112,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (MODE != MNRF_GEMM_WGRAD) prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < NUM_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], side ? 1 + NUM_EPI_WARPS : 1);
+      mbar_init(&mdone_bar[i], 1);
+    }
     for (int i = 0; i < NUM_ACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTAS * NUM_EPI_WARPS * 32); }
     fence_barrier_init();
   }
@@ -197,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             umma_bf16<CTAS>(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit<CTAS>(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
+          if (side) umma_commit<CTAS>(&mdone_bar[stage]);     // ... after the side sums have read it too
           if (kb == kb1 - 1) umma_commit<CTAS>(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
@@ -223,6 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float csodd[4] = {0.f, 0.f, 0.f, 0.f};     // tiles 1, 3, 5, ... (period 2)
     int cs_ncol0 = -1, cs_ncol1 = -1;
     uint32_t store_it = 0;
+    uint32_t sstage = 0, sphase = 0;        // WGRAD side sums: this warp's position in the operand ring
 
     // per-row inputs of a tile (DGRAD): fetched one tile ahead so their latency hides behind the
     // previous tile's epilogue
@@ -268,6 +281,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
       for (int w = 0; w < 4; ++w) mbits[w] = mb_next[w];
       fetch_row_inputs(tile + num_workers);
+      if (kWgrad && side) {
+        // Consume this tile's operand stages right behind the MMAs: column sums of the B tile (dY -> bias
+        // gradient; one output-row unit per column block does it) and row-weighted column sums of the A tile
+        // (X -> gradient of a Dense(1) head on the same activation; the first column block does it).
+        // MN-major stage layout: 64-wide atoms of [64 reduction rows x 128 B], SWIZZLE_128B.
+        const int split = rest / num_m_units;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kblocks_per_split);
+        const bool do_b = p.side_bsum != nullptr && (rest % num_m_units) == 0;
+        const bool do_a = p.side_aw != nullptr && n_blk == 0;
+        const int t = ew * 32 + lane;
+        const int b_rows_ = p.block_n / CTAS;
+        const int b_pairs = b_rows_ >> 1, b_rpg = 64 / (256 / b_pairs);
+        const int bp = t % b_pairs, bg = t / b_pairs;
+        const int ap = t & 63, ag = t >> 6;                    // A: 128 columns = 64 pairs x 4 row groups of 16
+        const uint32_t b_off = (uint32_t)((bp >> 5) * (BLOCK_K * 128) + ((bp & 3) << 2));
+        const uint32_t a_off = (uint32_t)((ap >> 5) * (BLOCK_K * 128) + ((ap & 3) << 2));
+        const int b_chunk = (bp & 31) >> 2, a_chunk = (ap & 31) >> 2;
+        float bs0 = 0.f, bs1 = 0.f, as0 = 0.f, as1 = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&mdone_bar[sstage], sphase, 6);
+          if (do_b) {
+            const uint8_t* sbp = smem_b + sstage * B_STAGE + b_off;
+#pragma unroll 8
+            for (int i = 0; i < b_rpg; ++i) {
+              const int r = bg * b_rpg + i;
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(sbp + r * 128 + ((b_chunk ^ (r & 7)) << 4));
+              bs0 += bf16_lo(w);
+              bs1 += bf16_hi(w);
+            }
+          }
+          if (do_a) {
+            const uint8_t* sap = smem_a + sstage * A_STAGE_BYTES + a_off;
+            const int64_t r0 = (int64_t)kb * BLOCK_K + ag * 16;
+#pragma unroll 8
+            for (int i = 0; i < 16; ++i) {
+              const int r = ag * 16 + i;
+              const float wr = (r0 + i < p.k) ? __ldg(p.side_w + r0 + i) : 0.f;
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(sap + r * 128 + ((a_chunk ^ (r & 7)) << 4));
+              as0 += wr * bf16_lo(w);
+              as1 += wr * bf16_hi(w);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[sstage]);
+          if (++sstage == NUM_STAGES) { sstage = 0; sphase ^= 1; }
+        }
+        if (do_b) {
+          float* dst = p.side_bsum + n_blk * p.block_n + rank * b_rows_ + (bp >> 5) * 64 + ((bp & 31) << 1);
+          atomicAdd(dst, bs0);
+          atomicAdd(dst + 1, bs1);
+        }
+        if (do_a) {
+          const int64_t mo = (int64_t)m_blk * BLOCK_M + (ap >> 5) * 64 + ((ap & 31) << 1);
+          if (mo < p.m) atomicAdd(p.side_aw + mo, as0);
+          if (mo + 1 < p.m) atomicAdd(p.side_aw + mo + 1, as1);
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N;
@@ -469,7 +540,8 @@ static int pick_block_n(int n) {
 
 int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16* b, const float* bias,
                    const float* rowv, const float* colv, const mnrf_bf16* mask, uint32_t* maskbits,
-                   float* colsum, const mnrf_bf16* addend, void* out, cudaStream_t stream) {
+                   float* colsum, const mnrf_bf16* addend, float* side_bsum, const float* side_w, float* side_aw,
+                   void* out, cudaStream_t stream) {
   // K-major modes: the reduction index is the contiguous one and layers are padded to 64.  WGRAD reduces
   // over the sample rows, any count: the last 64-row block is zero-filled by TMA past the tensor's end.
   MNRF_CHECK(d->mode == MNRF_GEMM_WGRAD || d->k % BLOCK_K == 0,
@@ -496,6 +568,8 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   p.ldadd = d->ldadd;
   if (addend) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD && d->ldadd % 8 == 0 && ((uintptr_t)addend % 16) == 0,
                          "mnrf_gemm(tc): addend is a DGRAD input with 16-byte aligned rows");
+  p.side_bsum = side_bsum; p.side_w = side_w; p.side_aw = side_aw;
+  if (side_bsum || side_aw) MNRF_CHECK(d->mode == MNRF_GEMM_WGRAD, "mnrf_gemm(tc): side sums belong to WGRAD");
   p.colsum = colsum;
   if (colsum) MNRF_CHECK(d->mode == MNRF_GEMM_DGRAD && p.block_n % 32 == 0,
                          "mnrf_gemm(tc): colsum is a DGRAD output and needs N %% 32 == 0");

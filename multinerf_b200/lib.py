@@ -119,6 +119,7 @@ _SIGNATURES = {
     'mnrf_viewdir_enc': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
                                    C.c_int32, _P]),
     'mnrf_gemm': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 11),
+    'mnrf_gemm_wgrad': (C.c_int, [C.POINTER(GemmDesc)] + [_P] * 7),
     'mnrf_mlp_chain': (C.c_int, [C.POINTER(ChainDesc), _P]),
     'mnrf_mlp_chain_max_layers': (C.c_int, []),
     'mnrf_head_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P, _P]),

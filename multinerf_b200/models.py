@@ -660,7 +660,7 @@ class Model:
     layers = []
     for j, i in enumerate(range(len(trunk) - 1, 0, -1)):
       sp = trunk[i]
-      ly = dict(w=mlp.w_kn[sp.name], maskbits=st.bits[i - 1], colsum=mlp.b(trunk[i - 1], g), out=dyl[i - 1])
+      ly = dict(w=mlp.w_kn[sp.name], maskbits=st.bits[i - 1], out=dyl[i - 1])
       if j == 0:
         ly.update(n_stream=W // 64, stream_col0=0, stream_kb0=0)
       else:
@@ -836,8 +836,10 @@ class Model:
   def _mlp_backward(self, st: LevelState, mlp: MLPDevice, rays=None, impl=0, loss_mults=None, stats=None):
     """Accumulates parameter gradients of one level into mlp.grads (fp32).
 
-    Bias gradients are column sums of the dY buffers; each is reduced inside the kernel that
-    PRODUCES that dY (DGRAD epilogue `colsum`, head_bwd `dxsum`), never by a separate pass.
+    Bias gradients are column sums of the dY buffers: each layer's weight-gradient GEMM takes them from the dY
+    tiles its main loop stages (`mnrf_gemm_wgrad` `bsum`), so neither a separate pass nor the dgrad epilogues
+    pay for them; the Dense(1) density head's weight gradient rides in the bottleneck's weight gradient the
+    same way (`side_aw`).
     """
     plan = mlp.plan
     cfg = plan.cfg
@@ -873,12 +875,13 @@ class Model:
       bw = bt.out_dim
       dcur = sc.dv[0]
       ops.head_bwd(st.v_last, mlp.w_nk[r.name], st.d_raw_rgb.view(M, 3), r.out_dim, r.in_pad, dx=dcur,
-                   relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g), dxsum=mlp.b(views[-1], g))
+                   relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g))
       have_skip_grad = False
       for i in range(len(views) - 1, -1, -1):
         sp = views[i]
         xin = st.vin if i == 0 else st.vacts[i - 1]
-        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(sp, g), m=sp.in_pad, n=Wv, k=M, impl=impl)
+        # every layer's bias gradient = column sums of its dY, taken from the tiles its weight gradient stages
+        ops.gemm_wgrad(xin, dcur, mlp.W(sp, g), m=sp.in_pad, n=Wv, k=M, bsum=mlp.b(sp, g), impl=impl)
         if i > 0:
           if (i - 1) in plan.view_concat_after:
             # this layer also consumed vin (skip concat): its second gradient contribution
@@ -887,15 +890,13 @@ class Model:
             have_skip_grad = True
           nxt = sc.dv[1] if dcur is sc.dv[0] else sc.dv[0]
           ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[sp.name], nxt, m=M, n=Wv, k=Wv,
-                   maskbits=st.vbits[i - 1], colsum=mlp.b(views[i - 1], g), impl=impl)
+                   maskbits=st.vbits[i - 1], impl=impl)
           dcur = nxt
       s0 = views[0]
       if plan.ref_stage:
         # full d vin: [ d bottleneck | d direction encoding (| d n.v) ]
         ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], sc.d_vin, m=M, n=plan.vin_pad, k=Wv,
                  addend=sc.d_vin_skip if have_skip_grad else None, impl=impl)
-        # bias gradient of the bottleneck = column sums of d vin[:, :bw]
-        ops.colsum(sc.d_vin[:, :bw], bw, mlp.b(bt, g))
         d_glo_ref = None
         if plan.glo_features > 0 and st.glo_vec is not None:     # before the slab columns are re-used
           g0 = plan.glo_col0
@@ -915,10 +916,12 @@ class Model:
           if sp is not None:
             ops.head_bwd(x_last, mlp.w_nk[sp.name], st.d_heads[role], sp.out_dim, sp.in_pad, dx=None,
                          dw=mlp.W(sp, g), db=mlp.b(sp, g))
-        ops.gemm(L.GEMM_WGRAD, x_last, sc.d_vin[:, :bw], mlp.W(bt, g), m=bt.in_pad, n=bw, k=M, impl=impl)
+        # bottleneck dW + db, and the Dense(1) density head's dW from the same x_last tiles
+        ops.gemm_wgrad(x_last, sc.d_vin[:, :bw], mlp.W(bt, g), m=bt.in_pad, n=bw, k=M, bsum=mlp.b(bt, g),
+                       side_w=st.d_raw_density.view(M), side_aw=mlp.W(d, g).view(-1), impl=impl)
         # d x_last = relu'(x_last) * ([d bottleneck | head gradients] @ [W_b | w_heads]^T)
         ops.gemm(L.GEMM_DGRAD, sc.d_vin, mlp.wcat_kn, dy, m=M, n=W, k=plan.vin_pad,
-                 maskbits=st.bits[-1], colsum=mlp.b(trunk[-1], g), impl=impl)
+                 maskbits=st.bits[-1], impl=impl)
       else:
         dbott = sc.d_vin[:, :bw]
         # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
@@ -926,17 +929,17 @@ class Model:
           # the GLO columns of vin carry gradient too: full-width dgrad, then sum over the samples
           ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], sc.d_vin, m=M, n=plan.vin_pad, k=Wv,
                    addend=sc.d_vin_skip if have_skip_grad else None, impl=impl)
-          ops.colsum(dbott, bw, mlp.b(bt, g))
         else:
           ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[s0.name], dbott, m=M, n=bw, k=Wv,
-                   colsum=mlp.b(bt, g), addend=sc.d_vin_skip[:, :bw] if have_skip_grad else None, impl=impl)
-        ops.gemm(L.GEMM_WGRAD, x_last, dbott, mlp.W(bt, g), m=bt.in_pad, n=bw, k=M, impl=impl)
+                   addend=sc.d_vin_skip[:, :bw] if have_skip_grad else None, impl=impl)
+        # bottleneck dW + db, and the Dense(1) density head's dW from the same x_last tiles (models.py:460,527)
+        ops.gemm_wgrad(x_last, dbott, mlp.W(bt, g), m=bt.in_pad, n=bw, k=M, bsum=mlp.b(bt, g),
+                       side_w=st.d_raw_density.view(M), side_aw=mlp.W(d, g).view(-1), impl=impl)
         # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
         ops.gemm(L.GEMM_DGRAD, dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bw,
-                 rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1],
-                 colsum=mlp.b(trunk[-1], g), impl=impl)
-      ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=None, dw=mlp.W(d, g),
-                   db=mlp.b(d, g))
+                 rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1], impl=impl)
+      # bias gradient of the density head: a plain sum of d_raw_density
+      mlp.b(d, g).add_(st.d_raw_density.sum())
       if plan.glo_features > 0 and st.glo_vec is not None:
         g0 = plan.glo_col0
         d_glo = d_glo_ref if plan.ref_stage else \
@@ -945,7 +948,7 @@ class Model:
             0, rays.cam_idx[:, 0].long(), d_glo)
     else:
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=dy, relu_mask=True,
-                   dw=mlp.W(d, g), db=mlp.b(d, g), dxsum=mlp.b(trunk[-1], g))
+                   dw=mlp.W(d, g), db=mlp.b(d, g))
     if plan.density_normals:
       # adjoint of the tangent chain: H_last = relu'(x_last) * (d_rgd (x) w_density), three streams
       hcur, hoth = sc.h[0], sc.h[1]
@@ -968,18 +971,18 @@ class Model:
       for i in range(nl - 1, -1, -1):
         sp = trunk[i]
         xin = st.feat if i == 0 else st.acts[i - 1]
-        ops.gemm(L.GEMM_WGRAD, xin, dyl[i], mlp.W(sp, g), m=sp.in_pad, n=W, k=M, impl=impl)
+        ops.gemm_wgrad(xin, dyl[i], mlp.W(sp, g), m=sp.in_pad, n=W, k=M, bsum=mlp.b(sp, g), impl=impl)
       return
     cur, other = sc.dy[0], sc.dy[1]
     for i in range(len(trunk) - 1, -1, -1):
       sp = trunk[i]
       xin = st.feat if i == 0 else st.acts[i - 1]
-      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(sp, g), m=sp.in_pad, n=W, k=M, impl=impl)
+      ops.gemm_wgrad(xin, cur, mlp.W(sp, g), m=sp.in_pad, n=W, k=M, bsum=mlp.b(sp, g), impl=impl)
       if i > 0:
         # only the hidden part of the input carries gradient (features are constants:
         # stop_gradient(sdist), models.py:200-201)
         ops.gemm(L.GEMM_DGRAD, cur, mlp.w_kn[sp.name], other, m=M, n=W, k=W,
-                 maskbits=st.bits[i - 1], colsum=mlp.b(trunk[i - 1], g), impl=impl)
+                 maskbits=st.bits[i - 1], impl=impl)
         cur, other = other, cur
 
 

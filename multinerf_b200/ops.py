@@ -149,7 +149,25 @@ def gemm(mode, a, b, out, *, m, n, k, act=L.ACT_NONE, bias=None, rowv=None, colv
   return out
 
 
-CHAIN_EVENTS_FLOPS = True
+def gemm_wgrad(x, dy, out, *, m, n, k, bsum=None, side_w=None, side_aw=None, impl=0):
+  """dW[m, n] += x[k, m]^T dy[k, n], plus (optional) bsum[n] += column sums of dy (the layer's bias gradient) and
+  side_aw[m] += sum_r side_w[r] x[r, m] (weight gradient of a Dense(1) head on x) -- include/mnrf.h."""
+  lib = L.load()
+  assert x.stride(-1) == 1 and dy.stride(-1) == 1 and out.stride(-1) == 1
+  d = L.GemmDesc(L.GEMM_WGRAD, L.ACT_NONE, m, n, k, x.stride(0), dy.stride(0), out.stride(0), 0, 0, 0, 0, impl)
+  _count()
+  ev = None
+  if GEMM_EVENTS is not None:
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[0].record()
+  L.check(lib.mnrf_gemm_wgrad(C.byref(d), L.ptr(x), L.ptr(dy), L.ptr(bsum), L.ptr(_f32(side_w)), L.ptr(side_aw),
+                              L.ptr(out), L.stream_ptr()))
+  if ev is not None:
+    ev[1].record()
+    GEMM_EVENTS.append((ev[0], ev[1], 2.0 * m * n * k))
+  return out
+
+
 
 
 def chain_desc(mode, m, layers, *, stream=None, stream_cols=0, head_w=None, head_b=None, head_out=None):

@@ -111,12 +111,17 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
   # capturing the NCCL all-reduce inside the step graph hangs on this stack (torch 2.11 / NCCL 2.28, measured on
   # 2 x B200 in round 2): opt-in only
   GRAPH_NCCL = os.environ.get('MNRF_GRAPH_NCCL', '0') == '1'
+  EARLY_EXCHANGE = os.environ.get('MNRF_EARLY_EXCHANGE', '0') == '1'
 
   # Backward runs the levels last to first, so a module's gradient is final once the lowest level that
   # uses it is done: for 360.gin the NerfMLP segment (34.7 of 36 MB) is final after level 2 and its
   # all-reduce overlaps the two PropMLP backward levels.
   def early_segments(n_levels):
-    if decay_views:
+    # Opt-in (MNRF_EARLY_EXCHANGE=1).  Measured on 2 and 8 x B200 (round 2): overlapping the NerfMLP all-reduce with
+    # the PropMLP backward is a LOSS here -- the backward kernels are persistent, one CTA (pair) per SM with all of
+    # its shared memory, so they cannot share SMs with NCCL's channel CTAs; every overlapped kernel waits for the
+    # collective on the SMs it needs (8 GPUs: 4.55 ms/step overlapped vs 4.31 ms with the exchange after the backward).
+    if decay_views or not EARLY_EXCHANGE:
       return {}                      # weight decay touches every gradient after the last level
     first_use = {}
     for i in range(n_levels):

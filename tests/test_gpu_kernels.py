@@ -371,6 +371,43 @@ def test_gemm_wgrad(ops, impl, R, Mo, N):
   close(out, ref + 1.0, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad impl={impl}')
 
 
+@pytest.mark.parametrize('impl', [1, 0])
+@pytest.mark.parametrize('R,Mo,N', [(65536, 256, 256), (4096, 512, 256), (8192, 1024, 1024), (16384, 1280, 256),
+                                    (2080, 128, 256), (1000, 320, 128), (37, 64, 64), (5000, 256, 64)])
+def test_gemm_wgrad_side_sums(ops, impl, R, Mo, N):
+  """mnrf_gemm_wgrad: the weight gradient plus the bias gradient (column sums of dY) and the gradient of a
+  Dense(1) head on the same activation, both taken from the operand tiles of the main loop."""
+  rng = np.random.default_rng(R + 3 * Mo + N)
+  x = _bf(rng.normal(size=(R, Mo)).astype(np.float32))
+  dy = _bf(rng.normal(size=(R, N)).astype(np.float32))
+  w = torch.tensor(rng.normal(size=(R,)).astype(np.float32))
+  out = torch.ones(Mo, N, device='cuda')
+  bsum = torch.full((N,), 2.0, device='cuda')
+  aw = torch.full((Mo,), -1.0, device='cuda')
+  ops.gemm_wgrad(x.cuda(), dy.cuda(), out, m=Mo, n=N, k=R, bsum=bsum, side_w=w.cuda(), side_aw=aw, impl=impl)
+  torch.cuda.synchronize()
+  close(out, x.float().T @ dy.float() + 1.0, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'wgrad impl={impl}')
+  close(bsum, dy.float().sum(0) + 2.0, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'bias gradient impl={impl}')
+  close(aw, (x.float() * w[:, None]).sum(0) - 1.0, atol=2e-3 * math.sqrt(R), rtol=1e-4, msg=f'head dW impl={impl}')
+  # each side sum alone
+  b2 = torch.zeros(N, device='cuda')
+  o2 = torch.zeros(Mo, N, device='cuda')
+  ops.gemm_wgrad(x.cuda(), dy.cuda(), o2, m=Mo, n=N, k=R, bsum=b2, impl=impl)
+  close(b2, dy.float().sum(0), atol=2e-3 * math.sqrt(R), rtol=1e-4, msg='bias gradient alone')
+  close(o2, x.float().T @ dy.float(), atol=2e-3 * math.sqrt(R), rtol=1e-4, msg='wgrad with bsum only')
+  a3 = torch.zeros(Mo, device='cuda')
+  o3 = torch.zeros(Mo, N, device='cuda')
+  ops.gemm_wgrad(x.cuda(), dy.cuda(), o3, m=Mo, n=N, k=R, side_w=w.cuda(), side_aw=a3, impl=impl)
+  close(a3, (x.float() * w[:, None]).sum(0), atol=2e-3 * math.sqrt(R), rtol=1e-4, msg='head dW alone')
+  # strided operands (the activation lives inside a wider buffer)
+  xb = torch.zeros(R, Mo + 64, dtype=torch.bfloat16, device='cuda')
+  xb[:, :Mo] = x.cuda()
+  b4 = torch.zeros(N, device='cuda')
+  o4 = torch.zeros(Mo, N, device='cuda')
+  ops.gemm_wgrad(xb[:, :Mo], dy.cuda(), o4, m=Mo, n=N, k=R, bsum=b4, impl=impl)
+  close(o4, x.float().T @ dy.float(), atol=2e-3 * math.sqrt(R), rtol=1e-4, msg='strided x')
+
+
 def test_heads_and_colsum(ops):
   rng = np.random.default_rng(5)
   for M, K, n_out in [(1000, 1024, 1), (777, 128, 3), (300, 256, 4)]:
