@@ -836,10 +836,12 @@ class Model:
   def _mlp_backward(self, st: LevelState, mlp: MLPDevice, rays=None, impl=0, loss_mults=None, stats=None):
     """Accumulates parameter gradients of one level into mlp.grads (fp32).
 
-    Bias gradients are column sums of the dY buffers: each layer's weight-gradient GEMM takes them from the dY
-    tiles its main loop stages (`mnrf_gemm_wgrad` `bsum`), so neither a separate pass nor the dgrad epilogues
-    pay for them; the Dense(1) density head's weight gradient rides in the bottleneck's weight gradient the
-    same way (`side_aw`).
+    Bias gradients are column sums of the dY buffers, never a separate pass over HBM.  Where they come from is
+    chosen by what is measured to be free: for the 1024-wide layers the dgrad epilogue that PRODUCES the dY
+    (`colsum`, hidden under a K = 1024 main loop); for chained 256-wide trunks the weight-gradient GEMM, whose
+    idle epilogue warps read the dY tiles of its main loop (`mnrf_gemm_wgrad` `bsum`; those GEMMs are HBM-bound,
+    while the same trick costs a 1024-wide weight gradient +48 %).  The bottleneck's weight gradient also carries
+    the Dense(1) density head's weight gradient (`side_aw`), which used to re-read the activation.
     """
     plan = mlp.plan
     cfg = plan.cfg
@@ -862,6 +864,8 @@ class Model:
       st.bwd = bw_
     sc = st.bwd
     g = mlp.grads
+    # bias gradients of the trunk come from its weight-gradient GEMMs when its dgrad chain is one launch
+    side = self._use_chain(plan, M, impl) and len(plan.by_role('trunk')) > 1
     d = plan.one('density')
     trunk = plan.by_role('trunk')
     x_last = st.x_last
@@ -875,13 +879,12 @@ class Model:
       bw = bt.out_dim
       dcur = sc.dv[0]
       ops.head_bwd(st.v_last, mlp.w_nk[r.name], st.d_raw_rgb.view(M, 3), r.out_dim, r.in_pad, dx=dcur,
-                   relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g))
+                   relu_mask=True, dw=mlp.W(r, g), db=mlp.b(r, g), dxsum=mlp.b(views[-1], g))
       have_skip_grad = False
       for i in range(len(views) - 1, -1, -1):
         sp = views[i]
         xin = st.vin if i == 0 else st.vacts[i - 1]
-        # every layer's bias gradient = column sums of its dY, taken from the tiles its weight gradient stages
-        ops.gemm_wgrad(xin, dcur, mlp.W(sp, g), m=sp.in_pad, n=Wv, k=M, bsum=mlp.b(sp, g), impl=impl)
+        ops.gemm(L.GEMM_WGRAD, xin, dcur, mlp.W(sp, g), m=sp.in_pad, n=Wv, k=M, impl=impl)
         if i > 0:
           if (i - 1) in plan.view_concat_after:
             # this layer also consumed vin (skip concat): its second gradient contribution
@@ -890,7 +893,7 @@ class Model:
             have_skip_grad = True
           nxt = sc.dv[1] if dcur is sc.dv[0] else sc.dv[0]
           ops.gemm(L.GEMM_DGRAD, dcur, mlp.w_kn[sp.name], nxt, m=M, n=Wv, k=Wv,
-                   maskbits=st.vbits[i - 1], impl=impl)
+                   maskbits=st.vbits[i - 1], colsum=mlp.b(views[i - 1], g), impl=impl)
           dcur = nxt
       s0 = views[0]
       if plan.ref_stage:
@@ -921,7 +924,7 @@ class Model:
                        side_w=st.d_raw_density.view(M), side_aw=mlp.W(d, g).view(-1), impl=impl)
         # d x_last = relu'(x_last) * ([d bottleneck | head gradients] @ [W_b | w_heads]^T)
         ops.gemm(L.GEMM_DGRAD, sc.d_vin, mlp.wcat_kn, dy, m=M, n=W, k=plan.vin_pad,
-                 maskbits=st.bits[-1], impl=impl)
+                 maskbits=st.bits[-1], colsum=None if side else mlp.b(trunk[-1], g), impl=impl)
       else:
         dbott = sc.d_vin[:, :bw]
         # d vin[:, :bw] = dcur * Wv0[:bw, :]^T  (no activation on the bottleneck)
@@ -937,7 +940,8 @@ class Model:
                        side_w=st.d_raw_density.view(M), side_aw=mlp.W(d, g).view(-1), impl=impl)
         # d x_last = (dbott * Wb^T + d_raw_density (x) w_density) * relu'(x_last)
         ops.gemm(L.GEMM_DGRAD, dbott, mlp.w_kn[bt.name], dy, m=M, n=W, k=bw,
-                 rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1], impl=impl)
+                 rowv=st.d_raw_density.view(M), colv=mlp.colv_density, maskbits=st.bits[-1],
+                 colsum=None if side else mlp.b(trunk[-1], g), impl=impl)
       # bias gradient of the density head: a plain sum of d_raw_density
       mlp.b(d, g).add_(st.d_raw_density.sum())
       if plan.glo_features > 0 and st.glo_vec is not None:
@@ -948,7 +952,7 @@ class Model:
             0, rays.cam_idx[:, 0].long(), d_glo)
     else:
       ops.head_bwd(x_last, mlp.w_nk[d.name], d_raw_density, 1, d.in_pad, dx=dy, relu_mask=True,
-                   dw=mlp.W(d, g), db=mlp.b(d, g))
+                   dw=mlp.W(d, g), db=mlp.b(d, g), dxsum=None if side else mlp.b(trunk[-1], g))
     if plan.density_normals:
       # adjoint of the tangent chain: H_last = relu'(x_last) * (d_rgd (x) w_density), three streams
       hcur, hoth = sc.h[0], sc.h[1]
@@ -977,12 +981,12 @@ class Model:
     for i in range(len(trunk) - 1, -1, -1):
       sp = trunk[i]
       xin = st.feat if i == 0 else st.acts[i - 1]
-      ops.gemm_wgrad(xin, cur, mlp.W(sp, g), m=sp.in_pad, n=W, k=M, bsum=mlp.b(sp, g), impl=impl)
+      ops.gemm(L.GEMM_WGRAD, xin, cur, mlp.W(sp, g), m=sp.in_pad, n=W, k=M, impl=impl)
       if i > 0:
         # only the hidden part of the input carries gradient (features are constants:
         # stop_gradient(sdist), models.py:200-201)
         ops.gemm(L.GEMM_DGRAD, cur, mlp.w_kn[sp.name], other, m=M, n=W, k=W,
-                 maskbits=st.bits[i - 1], impl=impl)
+                 maskbits=st.bits[i - 1], colsum=mlp.b(trunk[i - 1], g), impl=impl)
         cur, other = other, cur
 
 

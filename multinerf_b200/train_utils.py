@@ -98,13 +98,13 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     # the loss accumulators ride in the tail of the flat gradient buffer: one collective per step
     return params.stats_tail[:mcfg.num_levels * 8].view(mcfg.num_levels, 8)
   scratch = torch.zeros(4, device=dev)
-  dyn = torch.zeros(4, device=dev)               # lr, 1-b1^t, 1-b2^t
+  dyn = torch.zeros(4, device=dev)               # lr, 1-b1^t, 1-b2^t, annealing exponent: ONE H2D copy per step
   # Pinned staging ring for the per-step scalars: the host may run several graph replays ahead of the
   # device, so a slot is rewritten only after the H2D copy that last read it has completed (event).
   DYN_SLOTS = 8
   dyn_host = [torch.zeros(4).pin_memory() for _ in range(DYN_SLOTS)]
   dyn_events = [None] * DYN_SLOTS
-  anneal_dev = torch.zeros(1, device=dev)
+  anneal_dev = dyn[3:4]
   G = {'state': 0, 'fb': None, 'opt': None, 'rays': None, 'target': None, 'jitter': None,
        'noise': None, 'launches': 0}
   import os
@@ -236,7 +236,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     for mlp in model.mlps.values():
       mlp.repack()
 
-  def set_dyn(step, lr):
+  def set_dyn(step, lr, anneal=1.0):
     slot = G['dyn_slot'] = (G.get('dyn_slot', -1) + 1) % DYN_SLOTS
     if dyn_events[slot] is not None:
       dyn_events[slot].synchronize()
@@ -244,6 +244,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     h[0] = lr
     h[1] = 1.0 - config.adam_beta1 ** step
     h[2] = 1.0 - config.adam_beta2 ** step
+    h[3] = anneal
     dyn.copy_(h, non_blocking=True)
     if dyn_events[slot] is None:
       dyn_events[slot] = torch.cuda.Event()
@@ -255,9 +256,18 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       return None
     jit = G['jitter']
     if jit is None:
-      jit = [torch.empty((B,) if mcfg.single_jitter else (B, lv['S']), device=dev) for lv in sched]
+      # all levels' draws live in one flat buffer each: one RNG launch per step instead of one per level
+      def views(shapes):
+        sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+        flat = torch.empty(sum(sizes), device=dev)
+        out, o = [], 0
+        for sh, n_ in zip(shapes, sizes):
+          out.append(flat[o:o + n_].view(sh))
+          o += n_
+        return flat, out
+      G['jitter_flat'], jit = views([(B,) if mcfg.single_jitter else (B, lv['S']) for lv in sched])
       G['jitter'] = jit
-      G['noise'] = [torch.empty(B, lv['S'], device=dev) for lv in sched]
+      G['noise_flat'], G['noise'] = views([(B, lv['S']) for lv in sched])
     out = {'jitter': jit}
     need_noise = any(p.cfg.density_noise > 0 for p in model.plans.values())
     if isinstance(rng, dict):        # explicit draws: stage them in the static buffers
@@ -267,11 +277,9 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
         for t, src in zip(G['noise'], rng['density_noise']):
           t.copy_(torch.as_tensor(src).to(dev).reshape(t.shape), non_blocking=True)
     else:
-      for t in jit:
-        t.uniform_(0.0, 1.0, generator=rng)
+      G['jitter_flat'].uniform_(0.0, 1.0, generator=rng)
       if need_noise:
-        for t in G['noise']:
-          t.normal_(0.0, 1.0, generator=rng)
+        G['noise_flat'].normal_(0.0, 1.0, generator=rng)
     if need_noise:
       out['density_noise'] = G['noise']
     return out
@@ -309,8 +317,7 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
     if G['B'] != B:
       raise ValueError(f'graph mode needs a fixed batch size ({G["B"]} rays per rank), got {B}')
     rand = draw_randomness(rng, B, sched)
-    anneal_dev.fill_(_anneal(mcfg, train_frac))
-    set_dyn(params.step, lr)
+    set_dyn(params.step, lr, _anneal(mcfg, train_frac))
     if G['state'] == 1:
       # capture: inputs live in static buffers from now on
       import dataclasses
@@ -358,13 +365,20 @@ def create_train_step(model: models.Model, config: configs.Config, impl=0, use_g
       G['state'] = 2
     else:
       import dataclasses
-      for f in dataclasses.fields(rays):
-        v = getattr(rays, f.name)
+      # one fused multi-tensor copy of the step's inputs into the graph's static buffers
+      dsts, srcs = [G['target']], [target]
+      for name in [f.name for f in dataclasses.fields(rays)] + ['radii_flat', 'near_flat', 'far_flat']:
+        v = getattr(rays, name)
         if v is not None:
-          getattr(G['rays'], f.name).copy_(v, non_blocking=True)
-      for extra in ('radii_flat', 'near_flat', 'far_flat'):
-        getattr(G['rays'], extra).copy_(getattr(rays, extra), non_blocking=True)
-      G['target'].copy_(target, non_blocking=True)
+          dsts.append(getattr(G['rays'], name))
+          srcs.append(v)
+      by_dtype = {}
+      for d_, s_ in zip(dsts, srcs):
+        by_dtype.setdefault((d_.dtype, s_.dtype), ([], []))
+        by_dtype[(d_.dtype, s_.dtype)][0].append(d_)
+        by_dtype[(d_.dtype, s_.dtype)][1].append(s_)
+      for (dd, ss) in by_dtype.values():
+        torch._foreach_copy_(dd, ss, non_blocking=True)
     G['fb'].replay()
     if G['opt'] is not None:
       if G['split'] is not None:

@@ -12,6 +12,11 @@ echo "=== reference arm"; timeout 600 python bench.py --impl reference --steps 2
 echo "=== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
   --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no_cpu_baseline --no_graph > gpurun_out/launches_run.log 2>&1
+echo "=== ncu launch list, side sums as separate passes (A/B)"
+MNRF_SIDE_SUMS=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
+  --log-file gpurun_out/launches_noside.csv python bench.py --steps 1 --warmup 3 --no_cpu_baseline --no_graph > /dev/null 2>&1
+echo "=== bench train360 A/B same box"
+for v in 1 0 1 0; do MNRF_SIDE_SUMS=$v timeout 600 python bench.py --steps 10 --warmup 3 --no_cpu_baseline 2>&1 | tail -1 | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('side_sums=$v', round(j['ms_per_step'],3), 'ms/step', j['clocks'])"; done
 echo "=== ncu per-launch traffic of the tensor-core kernels (4th step)"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,lts__t_bytes.sum \
   --clock-control none -k regex:"gemm_tc_kernel|mlp_chain_kernel" -s 123 -c 41 --csv --log-file gpurun_out/gemm_traffic.csv \
