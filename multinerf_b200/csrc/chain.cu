@@ -77,6 +77,7 @@ struct ChainParams {
   const float* head_w;      // FWD: Dense(1) on the last layer's output (density head), fp32 copy of the bf16 row
   const float* head_b;
   float* head_out;
+  int prefetch;             // pull the next unit's streamed tiles into L2 ahead of time (render form only)
   long long* trace;         // -DMNRF_TIMING_KNOBS + MNRF_CHAIN_TRACE=<device ptr>: clock64 event log of CTA 0
   int debug;                // MNRF_CHAIN_DEBUG (timing experiments, -DMNRF_TIMING_KNOBS builds only; results are wrong):
                             // 1 = no epilogue math/smem writes, 2 = no bulk stores, 4 = no mask / head global writes
@@ -171,8 +172,11 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       };
       for (int64_t unit = pair; unit < p.num_units; unit += num_pairs) {
         // The streamed operand comes from HBM: with three k-blocks in flight (1.5k cycles of MMA work) a cold
-        // DRAM access (~3k cycles) would stall the first layer, so the NEXT unit's tiles are pulled into L2 now.
-        if (unit + num_pairs < p.num_units) {
+        // DRAM access (~3k cycles) stalls the first layer, so the NEXT unit's tiles are pulled into L2 now -- but
+        // only in the render form.  With every layer's activations streaming out through L2 (training form,
+        // backward) the prefetched lines are evicted before they are used and the operand is read from DRAM
+        // twice (ncu: 1.98 GB read for 1.07 GB of features), on a launch that is HBM-bound to begin with.
+        if (p.prefetch && unit + num_pairs < p.num_units) {
           for (int j = 0; j < p.num_layers; ++j) {
             const ChainLayer& L = p.layer[j];
             for (int X = 0; X < 2; ++X) {
@@ -516,6 +520,11 @@ extern "C" int mnrf_mlp_chain(const mnrf_chain_desc* d, mnrf_stream stream_) {
     if (make_tmap(&maps.stream, d->stream, d->m, d->stream_cols, d->ldstream, 64, 128)) return 1;
   }
   p.head_w = d->head_w; p.head_b = d->head_b; p.head_out = d->head_out;
+  {
+    int stores = 0;
+    for (int j = 0; j < d->num_layers; ++j) stores += d->layer[j].out ? 1 : 0;
+    p.prefetch = (d->mode == MNRF_CHAIN_FWD && stores <= 1) ? 1 : 0;
+  }
 #ifdef MNRF_TIMING_KNOBS
   p.debug = getenv("MNRF_CHAIN_DEBUG") ? atoi(getenv("MNRF_CHAIN_DEBUG")) : 0;
   p.trace = getenv("MNRF_CHAIN_TRACE") ? reinterpret_cast<long long*>(strtoull(getenv("MNRF_CHAIN_TRACE"), nullptr, 0)) : nullptr;

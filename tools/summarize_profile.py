@@ -86,7 +86,7 @@ if os.path.exists(tp):
   with open(os.path.join(out_dir, f'{tag}_gemm_traffic.txt'), 'w') as f:
     f.write('# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,'
             'sm__pipe_tensor_cycles_active...,lts__t_bytes.sum --clock-control none\n')
-    f.write(f'# every gemm_tc_kernel launch of one 360.gin train step (16384 rays): {len(rows)} launches, '
+    f.write(f'# every tensor-core launch (gemm_tc_kernel + mlp_chain_kernel) of one 360.gin train step (16384 rays): {len(rows)} launches, '
             f'DRAM {sum(tot) / 1e9:.2f} GB per step, {sum(tot) / len(tot) / 1e9:.4f} GB per launch on average\n')
     f.write('#  i  kernel<mode,ctas,stages,out>            time_us  dram_rd_MB  dram_wr_MB  L2_GB  tensor_pipe_%\n')
     for i, r in enumerate(rows):
@@ -95,8 +95,8 @@ if os.path.exists(tp):
               f"{r.get('lts__t_bytes.sum', 0) / 1e9:7.2f} "
               f"{r.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0):8.1f}\n")
   with open(os.path.join(out_dir, 'gemm_tc_traffic.json'), 'w') as f:
-    json.dump({'kernel': 'gemm_tc_kernel', 'launches': len(tot), 'dram_bytes_per_launch': sum(tot) / len(tot),
+    json.dump({'kernel': 'gemm_tc_kernel + mlp_chain_kernel', 'launches': len(tot), 'dram_bytes_per_launch': sum(tot) / len(tot),
                'dram_bytes_per_step': sum(tot),
                'source': f'profiles/{tag}_gemm_traffic.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum, '
-                         'every GEMM launch of one 360.gin train step)'}, f, indent=1)
+                         'every tensor-core launch of one 360.gin train step)'}, f, indent=1)
   print('wrote gemm_tc_traffic.json:', sum(tot) / len(tot) / 1e9, 'GB per launch,', sum(tot) / 1e9, 'GB per step')
