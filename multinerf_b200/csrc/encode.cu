@@ -9,6 +9,8 @@
 //
 // Output: bf16 feature rows written straight into the MLP's input buffer (row stride
 // ld_feat), staged through shared memory so that each lane stores 16 B.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mnrf {
@@ -215,8 +217,10 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   return r;
 }
 
+// A ray may be split into `nseg` segments of `seg_len` samples (a multiple of G), one warp each: with few rays per
+// launch (a 2048-ray shard of an 8-GPU step) one warp per ray leaves most of the machine idle.
 __global__ void __launch_bounds__(256)
-encode_fast_kernel(mnrf_encode_desc d, int G, const float* __restrict__ sdist,
+encode_fast_kernel(mnrf_encode_desc d, int G, int nseg, int seg_len, const float* __restrict__ sdist,
                    const float* __restrict__ origins, const float* __restrict__ directions,
                    const float* __restrict__ radii, const float* __restrict__ near,
                    const float* __restrict__ far, const float* __restrict__ basis,
@@ -240,21 +244,25 @@ encode_fast_kernel(mnrf_encode_desc d, int G, const float* __restrict__ sdist,
   const float sc0 = __int_as_float((127 + d.min_deg) << 23);       // 2^min_deg
   const int chunks = row_bytes / 16;
 
-  for (int ray = blockIdx.x * nw + wib; ray < d.num_rays; ray += gridDim.x * nw) {
+  const int64_t num_items = (int64_t)d.num_rays * nseg;
+  for (int64_t item = (int64_t)blockIdx.x * nw + wib; item < num_items; item += (int64_t)gridDim.x * nw) {
+    const int ray = (int)(item / nseg);
+    const int s_begin = (int)(item - (int64_t)ray * nseg) * seg_len;
+    const int s_end = min(S, s_begin + seg_len);
     const float o[3] = {origins[ray * 3 + 0], origins[ray * 3 + 1], origins[ray * 3 + 2]};
     const float dv[3] = {directions[ray * 3 + 0], directions[ray * 3 + 1], directions[ray * 3 + 2]};
     const float radius = radii[ray];
     const float s_near = fwd_raydist(d.raydist_fn, near[ray]);
     const float s_far = fwd_raydist(d.raydist_fn, far[ray]);
     __syncwarp();
-    for (int i = lane; i <= S; i += 32) {
+    for (int i = s_begin + lane; i <= s_end; i += 32) {
       float t = s_to_t(d.raydist_fn, sdist[(size_t)ray * (S + 1) + i], s_near, s_far);
       tds[i] = t;
       if (tdist_out) tdist_out[(size_t)ray * (S + 1) + i] = t;
     }
     __syncwarp();
     // phase A: one lane per sample -- Gaussian of the frustum, contracted
-    for (int s = lane; s < S; s += 32) {
+    for (int s = s_begin + lane; s < s_end; s += 32) {
       Gauss g;
       cast_one(d.ray_shape, tds[s], tds[s + 1], o, dv, radius, g);
       if (d.warp_contract) contract_gauss(g);
@@ -267,8 +275,8 @@ encode_fast_kernel(mnrf_encode_desc d, int G, const float* __restrict__ sdist,
     }
     __syncwarp();
     // phase B: G samples at a time
-    for (int s0 = 0; s0 < S; s0 += G) {
-      const int g = min(G, S - s0);
+    for (int s0 = s_begin; s0 < s_end; s0 += G) {
+      const int g = min(G, s_end - s0);
       for (int j = lane; j < g * K; j += 32) {
         const int sl = j / K;
         const int k = j - sl * K;
@@ -332,6 +340,42 @@ __global__ void viewdir_enc_kernel(int num_rays, int S, int deg, const float* __
   }
 }
 
+// Same values, computed ONCE per ray (they do not depend on the sample) and replicated over the ray's S rows with
+// 16-byte stores: one warp per ray, the slab row staged in shared memory.  Needs a 16-byte aligned slab.
+__global__ void __launch_bounds__(256)
+viewdir_enc_rows_kernel(int num_rays, int S, int deg, const float* __restrict__ viewdirs,
+                        __nv_bfloat16* __restrict__ out, int ld, int col0, int col_end) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int width = col_end - col0;                 // multiple of 8
+  const int chunks = width / 8;                     // 16-byte chunks per row
+  __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(smem_raw) + (size_t)wib * width;
+  for (int ray = blockIdx.x * nw + wib; ray < num_rays; ray += gridDim.x * nw) {
+    __syncwarp();
+    for (int c = lane; c < width; c += 32) {
+      float v = 0.f;
+      if (c < 3) {
+        v = viewdirs[ray * 3 + c];
+      } else if (c < 3 + 6 * deg) {
+        int f = c - 3;
+        const int half = f / (3 * deg);
+        f -= half * 3 * deg;
+        const int l = f / 3, ch = f - l * 3;
+        const float x = viewdirs[ray * 3 + ch] * exp2f((float)l);
+        v = sinf(half ? x + 1.57079637050628662109375f : x);   // plain sin (coord.py:143-144)
+      }
+      row[c] = __float2bfloat16(v);
+    }
+    __syncwarp();
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+    __nv_bfloat16* dst0 = out + (size_t)ray * S * (size_t)ld + col0;
+    for (int i = lane; i < S * chunks; i += 32) {
+      const int r = i / chunks, c = i - r * chunks;
+      reinterpret_cast<uint4*>(dst0 + (size_t)r * ld)[c] = src[c];
+    }
+  }
+}
+
 }  // namespace mnrf
 
 static int encode_impl(const mnrf_encode_desc* d, const float* sdist, const float* origins,
@@ -374,8 +418,16 @@ static int encode_impl(const mnrf_encode_desc* d, const float* sdist, const floa
                   (size_t)nw * G * row_bytes;
     MNRF_CHECK(smem <= 200 * 1024, "mnrf_encode: shared memory %zu too large", smem);
     MNRF_CUDA(cudaFuncSetAttribute(encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // segments per ray: enough warps to fill the machine ~4 deep when the launch has few rays
+    const int64_t want_warps = (int64_t)mnrf_num_sms() * nw * 4;
+    int nseg = (int)std::min<int64_t>((want_warps + d->num_rays - 1) / d->num_rays, std::max(1, d->num_samples / (2 * G)));
+    nseg = std::max(1, nseg);
+    int seg_len = (d->num_samples + nseg - 1) / nseg;
+    seg_len = (seg_len + G - 1) / G * G;
+    nseg = (d->num_samples + seg_len - 1) / seg_len;
+    blocks = (int)std::min<int64_t>(((int64_t)d->num_rays * nseg + nw - 1) / nw, max_blocks);
     encode_fast_kernel<<<blocks, nw * 32, smem, (cudaStream_t)stream>>>(
-        *d, G, sdist, origins, directions, radii, near, far, basis,
+        *d, G, nseg, seg_len, sdist, origins, directions, radii, near, far, basis,
         reinterpret_cast<__nv_bfloat16*>(feat_bf16), feat_f32, tdist_out);
     MNRF_LAUNCH_CHECK();
     return 0;
@@ -421,6 +473,14 @@ extern "C" int mnrf_viewdir_enc(int32_t num_rays, int32_t num_samples, int32_t d
   MNRF_CHECK(col_end - col0 >= 3 + 6 * deg && col_end <= ld, "mnrf_viewdir_enc: slab [%d,%d) too small for deg %d",
              col0, col_end, deg);
   if (num_rays == 0) return 0;
+  if ((col_end - col0) % 8 == 0 && col0 % 8 == 0 && ld % 8 == 0 && ((uintptr_t)out % 16) == 0) {
+    const int nw = 8;
+    const int blocks_r = std::min((num_rays + nw - 1) / nw, mnrf_num_sms() * 8);
+    viewdir_enc_rows_kernel<<<blocks_r, nw * 32, (size_t)nw * (col_end - col0) * 2, (cudaStream_t)stream>>>(
+        num_rays, num_samples, deg, viewdirs, reinterpret_cast<__nv_bfloat16*>(out), ld, col0, col_end);
+    MNRF_LAUNCH_CHECK();
+    return 0;
+  }
   size_t total = (size_t)num_rays * num_samples * (col_end - col0);
   int blocks = (int)((total + 255) / 256);
   int maxb = mnrf_num_sms() * 16;

@@ -125,6 +125,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (CTAS == 1) __syncthreads(); else cluster_sync_all();    // peers must see initialised barriers
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: this grid is persistent (every CTA resident from the start), so the next grid may
+  // take each SM the moment this grid's CTA leaves it; nothing above touched global memory, everything below does.
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int b_rows = p.block_n / CTAS;             // B-tile rows this CTA stages
   const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)b_rows * BLOCK_K * 2;
@@ -300,7 +304,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t a_off = (uint32_t)((ap >> 5) * (BLOCK_K * 128) + ((ap & 3) << 2));
         const int b_chunk = (bp & 31) >> 2, a_chunk = (ap & 31) >> 2;
         float bs0 = 0.f, bs1 = 0.f, as0 = 0.f, as1 = 0.f;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        // side_w rows of a k-block are a fresh 64-byte segment of global memory per warp: fetched kSidePf k-blocks
+        // ahead (lane i < 16 holds row i of this warp's 16-row group), or every k-block would expose one cold DRAM
+        // round trip on the path that releases the operand ring (measured: 2.1k cycles per k-block against 512 of
+        // MMA work on the bottleneck layer's weight gradient)
+        constexpr int kSidePf = 4;
+        float wq[kSidePf];
+        auto side_w_fetch = [&](int kbx) -> float {
+          const int64_t rr = (int64_t)kbx * BLOCK_K + ag * 16 + lane;
+          return (do_a && kbx < kb1 && lane < 16 && rr < p.k) ? __ldg(p.side_w + rr) : 0.f;
+        };
+#pragma unroll
+        for (int j = 0; j < kSidePf; ++j) wq[j] = side_w_fetch(kb0 + j);
+        for (int kbq = kb0; kbq < kb1; kbq += kSidePf) {
+#pragma unroll
+        for (int jq = 0; jq < kSidePf; ++jq) {
+          const int kb = kbq + jq;
+          if (kb >= kb1) break;
+          const float wcur = wq[jq];
+          wq[jq] = side_w_fetch(kb + kSidePf);
           mbar_wait(&mdone_bar[sstage], sphase, 6);
           if (do_b) {
             const uint8_t* sbp = smem_b + sstage * B_STAGE + b_off;
@@ -314,11 +336,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (do_a) {
             const uint8_t* sap = smem_a + sstage * A_STAGE_BYTES + a_off;
-            const int64_t r0 = (int64_t)kb * BLOCK_K + ag * 16;
 #pragma unroll 8
             for (int i = 0; i < 16; ++i) {
               const int r = ag * 16 + i;
-              const float wr = (r0 + i < p.k) ? __ldg(p.side_w + r0 + i) : 0.f;
+              const float wr = __shfl_sync(0xffffffffu, wcur, i);
               const uint32_t w = *reinterpret_cast<const uint32_t*>(sap + r * 128 + ((a_chunk ^ (r & 7)) << 4));
               as0 += wr * bf16_lo(w);
               as1 += wr * bf16_hi(w);
@@ -327,6 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty_bar[sstage]);
           if (++sstage == NUM_STAGES) { sstage = 0; sphase ^= 1; }
+        }
         }
         if (do_b) {
           float* dst = p.side_bsum + n_blk * p.block_n + rank * b_rows_ + (bp >> 5) * 64 + ((bp & 31) << 1);
@@ -585,6 +607,7 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   p.use_tma_store = (d->mode != MNRF_GEMM_WGRAD && p.block_n % 64 == 0) ? 1 : 0;
   static const int cfg_ctas = getenv("MNRF_GEMM_CTAS") ? atoi(getenv("MNRF_GEMM_CTAS")) : 2;
   static const int cfg_stages = getenv("MNRF_GEMM_STAGES") ? atoi(getenv("MNRF_GEMM_STAGES")) : 0;
+  static const int cfg_smallk = getenv("MNRF_GEMM_SMALLK") ? atoi(getenv("MNRF_GEMM_SMALLK")) : 0;
 #ifdef MNRF_TIMING_KNOBS
   // timing experiments only (results are wrong by construction): compiled in only on request
   static const int cfg_debug = getenv("MNRF_GEMM_DEBUG") ? atoi(getenv("MNRF_GEMM_DEBUG")) : 0;
@@ -598,9 +621,18 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
   const int workers = sms / ctas;
   p.num_splits = 1;
   if (d->mode == MNRF_GEMM_WGRAD) {
+    // Split the reduction over the sample rows so that (output tiles x splits) work items fill whole rounds of the
+    // workers -- with the FEWEST splits that do: every work item ends in a 256 x 256 fp32 red.add pass over its
+    // output tile, and for a one-tile weight gradient (PropMLP 256 x 256) those passes all hit the same 256 KB of
+    // L2.  (148 splits there cost a fixed ~25 us per launch -- ncu, 2048-ray shard: 48 us against 21 us of streaming.)
     const int out_tiles = (p.num_m_blocks / ctas) * p.num_n_blocks;
-    int splits = std::max(1, (2 * workers) / out_tiles);
-    splits = std::min(splits, p.num_k_blocks);
+    const int max_splits = std::min(std::max(1, (2 * workers) / out_tiles), p.num_k_blocks);
+    int splits = max_splits;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int items = out_tiles * sp;
+      const int rounds = (items + workers - 1) / workers;
+      if (items * 100 >= rounds * workers * 95) { splits = sp; break; }
+    }
     p.num_splits = splits;
   }
   p.kblocks_per_split = (p.num_k_blocks + p.num_splits - 1) / p.num_splits;
@@ -639,16 +671,25 @@ int gemm_tc_launch(const mnrf_gemm_desc* d, const mnrf_bf16* a, const mnrf_bf16*
     cudaLaunchConfig_t cfg = {};                                                                      \
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS);                                       \
     cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;                                                \
-    cudaLaunchAttribute attr[1];                                                                      \
+    cudaLaunchAttribute attr[2];                                                                      \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                 \
     attr[0].val.clusterDim.x = CTAS_; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;     \
-    cfg.attrs = attr; cfg.numAttrs = 1;                                                               \
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
+    attr[1].val.programmaticStreamSerializationAllowed = 1;                                           \
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;                                           \
     MNRF_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));                                         \
   } while (0)
+  // Ring depth vs output staging (CTA pairs): a K = 1024 tile spends 8k cycles in the main loop, so the deepest
+  // operand ring wins and one staging slab per epilogue warp is enough; a short-K tile (K <= 512: the bottleneck /
+  // view-branch input gradients) is paced by its epilogue, where a warp that owns ONE slab stalls on the bulk
+  // store that is still reading it -- those shapes take fewer operand stages and 2 or 3 slabs (MNRF_GEMM_SMALLK).
+  int stages_sel = cfg_stages;
+  if (stages_sel == 0 && d->mode != MNRF_GEMM_WGRAD && p.num_k_blocks <= 8) stages_sel = cfg_smallk;
 #define MNRF_LAUNCH_TC(MODE_)                                                                         \
   do {                                                                                                \
     if (ctas == 2) {                                                                                  \
-      if (cfg_stages == 5) MNRF_LAUNCH_TC2(MODE_, 2, 5, 2);                                           \
+      if (stages_sel == 5) MNRF_LAUNCH_TC2(MODE_, 2, 5, 2);                                           \
+      else if (stages_sel == 4) MNRF_LAUNCH_TC2(MODE_, 2, 4, 3);                                      \
       else MNRF_LAUNCH_TC2(MODE_, 2, 6, 1);                                                           \
     } else {                                                                                          \
       MNRF_LAUNCH_TC2(MODE_, 1, 4, 1);                                                                \

@@ -173,6 +173,153 @@ head_bwd_kernel(int64_t M, int K, const __nv_bfloat16* __restrict__ x, int64_t l
   }
 }
 
+// Narrow inputs (K = 64 or 128: the rgb head on the view MLP's output): a row is only LPR = K/8 sixteen-byte chunks,
+// so a warp-per-row mapping leaves half (or three quarters) of the lanes idle and one load in flight per warp.  Here
+// a warp covers 32/LPR rows per pass and U passes per iteration (U independent 16-byte loads per lane in flight);
+// row sums are butterfly reductions over the LPR lanes of a row (the same additions, in the same order, as the
+// full-warp butterfly of head_fwd_kernel with its idle lanes contributing zeros).
+template <int LPR, int U>
+__global__ void __launch_bounds__(256)
+head_fwd_sub_kernel(int64_t M, int n_out, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ b, float* __restrict__ raw) {
+  constexpr int K = LPR * 8, RW = 32 / LPR;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int sub = lane / LPR, c = lane % LPR;
+  float wv[kMaxHead][8];
+#pragma unroll
+  for (int o = 0; o < kMaxHead; ++o) {
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (o < n_out) t = __ldg(reinterpret_cast<const uint4*>(w + (size_t)o * K) + c);
+    const uint32_t tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { wv[o][2 * q] = bf16_lo(tt[q]); wv[o][2 * q + 1] = bf16_hi(tt[q]); }
+  }
+  float bv[kMaxHead];
+#pragma unroll
+  for (int o = 0; o < kMaxHead; ++o) bv[o] = (b && o < n_out) ? __ldg(b + o) : 0.f;
+  const int64_t step = (int64_t)gridDim.x * nw * (RW * U);
+  for (int64_t m0 = ((int64_t)blockIdx.x * nw + wib) * (RW * U); m0 < M; m0 += step) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = m0 + u * RW + sub;
+      v[u] = row < M ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx) + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = m0 + u * RW + sub;
+      const uint32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int o = 0; o < kMaxHead; ++o) {
+        if (o < n_out) {
+          float acc = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc += bf16_lo(vv[q]) * wv[o][2 * q] + bf16_hi(vv[q]) * wv[o][2 * q + 1];
+#pragma unroll
+          for (int sh = LPR / 2; sh > 0; sh >>= 1) acc += __shfl_xor_sync(kFull, acc, sh);
+          if (c == 0 && row < M) raw[row * n_out + o] = acc + bv[o];
+        }
+      }
+    }
+  }
+}
+
+template <int N_OUT, int LPR, int U>
+__global__ void __launch_bounds__(256)
+head_bwd_sub_kernel(int64_t M, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ draw,
+                    __nv_bfloat16* __restrict__ dx, int64_t lddx, int relu_mask,
+                    float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dxsum,
+                    int64_t rows_per_block) {
+  constexpr int K = LPR * 8, RW = 32 / LPR;
+  __shared__ float sdw[N_OUT * K];
+  __shared__ float sxs[K];
+  for (int i = threadIdx.x; i < N_OUT * K; i += blockDim.x) sdw[i] = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) sxs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int sub = lane / LPR, c = lane % LPR;
+  float wv[N_OUT][8];
+#pragma unroll
+  for (int o = 0; o < N_OUT; ++o) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(w + (size_t)o * K) + c);
+    const uint32_t tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { wv[o][2 * q] = bf16_lo(tt[q]); wv[o][2 * q + 1] = bf16_hi(tt[q]); }
+  }
+  float racc[N_OUT][8], dbacc[N_OUT], xsum[8];
+#pragma unroll
+  for (int o = 0; o < N_OUT; ++o) {
+    dbacc[o] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) racc[o][e] = 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) xsum[e] = 0.f;
+  const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m_end = min(M, m_begin + rows_per_block);
+  for (int64_t m0 = m_begin + (int64_t)wib * (RW * U); m0 < m_end; m0 += (int64_t)nw * (RW * U)) {
+    uint4 v[U];
+    float g[U][N_OUT];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = m0 + u * RW + sub;
+      const bool ok = row < m_end;
+      v[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx) + c) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int o = 0; o < N_OUT; ++o) g[u][o] = ok ? __ldg(draw + row * N_OUT + o) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = m0 + u * RW + sub;
+      const uint32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float xe[8], de[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { xe[2 * q] = bf16_lo(vv[q]); xe[2 * q + 1] = bf16_hi(vv[q]); }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) de[e] = 0.f;
+#pragma unroll
+      for (int o = 0; o < N_OUT; ++o) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          de[e] += g[u][o] * wv[o][e];
+          racc[o][e] += g[u][o] * xe[e];
+        }
+        if (c == 0) dbacc[o] += g[u][o];
+      }
+      if (dx && row < m_end) {
+        if (relu_mask) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) de[e] = xe[e] > 0.f ? de[e] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xsum[e] += de[e];
+        uint4 o4;
+        o4.x = pack_bf16(de[0], de[1]); o4.y = pack_bf16(de[2], de[3]);
+        o4.z = pack_bf16(de[4], de[5]); o4.w = pack_bf16(de[6], de[7]);
+        reinterpret_cast<uint4*>(dx + row * lddx)[c] = o4;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < N_OUT; ++o) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&sdw[o * K + c * 8 + e], racc[o][e]);
+    if (c == 0 && db && dbacc[o] != 0.f) atomicAdd(&db[o], dbacc[o]);
+  }
+  if (dxsum) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&sxs[c * 8 + e], xsum[e]);
+  }
+  __syncthreads();
+  // dw is in the master layout [K, n_out] (row-major), the staging buffer is [n_out][K]
+  if (dw) for (int i = threadIdx.x; i < N_OUT * K; i += blockDim.x) {
+    const int o = i / K, k = i - o * K;
+    atomicAdd(&dw[(size_t)k * N_OUT + o], sdw[i]);
+  }
+  if (dxsum) for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(&dxsum[i], sxs[i]);
+}
+
 // out[n] += sum_m x[m, n]
 __global__ void __launch_bounds__(256)
 colsum_kernel(int64_t M, int N, const __nv_bfloat16* __restrict__ x, int64_t ldx,
@@ -316,6 +463,17 @@ extern "C" int mnrf_head_fwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf1
   MNRF_CHECK(k % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0,
              "mnrf_head_fwd: K/ld must be multiples of 8 and pointers 16-byte aligned");
   if (m == 0) return 0;
+  if (k == 256 || k == 128 || k == 64) {
+    // rows of one / half / a quarter of a warp's 16-byte chunks: 4 independent loads in flight per lane
+    const int rows_per_block = 8 * (256 / k) * 4;
+    const int blocks = (int)std::min<int64_t>((m + rows_per_block - 1) / rows_per_block, (int64_t)mnrf_num_sms() * 8);
+#define MNRF_HFS(LPR_)                                                                                 \
+  head_fwd_sub_kernel<LPR_, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(                               \
+      m, n_out, reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(w), b, raw)
+    if (k == 256) MNRF_HFS(32); else if (k == 128) MNRF_HFS(16); else MNRF_HFS(8);
+    MNRF_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = (size_t)n_out * k * 2;
   int blocks = (int)std::min<int64_t>((m + 7) / 8, (int64_t)mnrf_num_sms() * 8);
   head_fwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
@@ -336,6 +494,26 @@ extern "C" int mnrf_head_bwd(int64_t m, int32_t k, int32_t n_out, const mnrf_bf1
   MNRF_CHECK(k % 8 == 0 && k <= 1536 && ldx % 8 == 0 && (!dx || lddx % 8 == 0),
              "mnrf_head_bwd: K must be a multiple of 8 and <= 1536");
   if (m == 0) return 0;
+  if ((k == 256 || k == 128 || k == 64) && ((uintptr_t)w % 16) == 0) {
+    // rows of one / half / a quarter of a warp's 16-byte chunks (see head_bwd_sub_kernel)
+    // every block ends with n_out*K + K global atomics on the same addresses: two blocks per SM keep enough loads
+    // in flight (8 warps x 4 x 512 B each) without serialising the flush (592 blocks: ~45 us of atomics per launch)
+    const int blocks_s = (int)std::min<int64_t>((m + 511) / 512, (int64_t)mnrf_num_sms() * 2);
+    const int64_t rpb_s = ((m + blocks_s - 1) / blocks_s + 7) / 8 * 8;
+#define MNRF_HBS(NO, LPR_)                                                                              \
+  head_bwd_sub_kernel<NO, LPR_, 4><<<blocks_s, 256, 0, (cudaStream_t)stream>>>(                         \
+      m, reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(w), draw, \
+      reinterpret_cast<__nv_bfloat16*>(dx), lddx, relu_mask, dw, db, dxsum, rpb_s)
+#define MNRF_HBS_N(NO) do { if (k == 256) MNRF_HBS(NO, 32); else if (k == 128) MNRF_HBS(NO, 16); else MNRF_HBS(NO, 8); } while (0)
+    switch (n_out) {
+      case 1: MNRF_HBS_N(1); break;
+      case 2: MNRF_HBS_N(2); break;
+      case 3: MNRF_HBS_N(3); break;
+      default: MNRF_HBS_N(4); break;
+    }
+    MNRF_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = (size_t)n_out * k * (4 + 2);
   MNRF_CHECK(smem <= 48 * 1024, "mnrf_head_bwd: n_out*K too large for the shared-memory staging");
   int blocks = (int)std::min<int64_t>((m + 7) / 8, (int64_t)mnrf_num_sms() * 4);

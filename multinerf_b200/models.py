@@ -322,6 +322,7 @@ class Model:
     self.mlps: Dict[str, MLPDevice] = {}
     self._levels: Dict[Any, LevelState] = {}
     self._u_cache = {}
+    self._init_hist = {}
 
   # ------------------------------------------------------------------ parameters
   def num_params(self):
@@ -705,10 +706,20 @@ class Model:
         off = self.params.seg('exposure_scaling_offsets').view(-1, 3)[eidx]
         rgb_scale = rgb_scale * (1 + mask * off)
       rgb_scale = rgb_scale.contiguous()
-    sdist_prev = torch.empty(B, 2, device=dev)
-    sdist_prev[:, 0] = s_near
-    sdist_prev[:, 1] = s_far
-    w_prev = torch.ones(B, 1, device=dev)
+    # the initial one-interval histogram [s_near, s_far] with weight 1 is a constant of (B, s_near, s_far): built
+    # once, so a captured step does not replay three fill kernels for it
+    ck = (B, float(s_near), float(s_far))
+    init = self._init_hist.get(ck)
+    if init is None:
+      sd0 = torch.empty(B, 2, device=dev)
+      sd0[:, 0] = s_near
+      sd0[:, 1] = s_far
+      init = (sd0, torch.ones(B, 1, device=dev))
+      # entries are never evicted (a captured graph may hold their addresses); with near-plane annealing s_near
+      # changes every step, so the table simply stops growing
+      if len(self._init_hist) < 8 and not torch.cuda.is_current_stream_capturing():
+        self._init_hist[ck] = init
+    sdist_prev, w_prev = init
     states = []
     for i, lv in enumerate(sched):
       mname = 'NerfMLP_0' if (m.single_mlp or not lv['is_prop']) else 'PropMLP_0'
