@@ -104,9 +104,6 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 #else
 #define CH_TRACE(tag, unit, j, X) do {} while (0)
 #endif
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }

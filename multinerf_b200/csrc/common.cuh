@@ -82,12 +82,26 @@ __device__ __forceinline__ float safe_sin_f(float x) {
   return sinf(x);
 }
 
+// rintf for |v| < 2^22 without the conversion pipe: adding 1.5 * 2^23 rounds v to an integer (nearest-even, the
+// add's own rounding) and the subtraction is exact.  FRND shares the quarter-rate unit with MUFU.SIN / MUFU.EX2,
+// which the IPE inner loop already keeps busy three instructions out of every ~30.
+__device__ __forceinline__ float rint_small(float v) {
+  return __fsub_rn(__fadd_rn(v, 12582912.f), 12582912.f);
+}
+
 // Same function for the bulk of the IPE features (1.3e9 evaluations per 360.gin step):
 //  * x mod fl32(100*pi) is reproduced EXACTLY without fmodf: k = floor(x/t) may be off by one, the
 //    remainder x - k*t is exact in one FMA (fmod results are representable), and the +-t fix-up is
 //    exact for the same reason;
 //  * sin of the reduced argument (|r| < 100*pi): Cody-Waite reduction by 2*pi (hi + lo, two FMAs)
 //    then MUFU.SIN (|arg| <= pi: abs error 2^-21.4).  Total abs error < 1e-6 (parity bar: 1e-5).
+// sin(x) for |x| < 100*pi (the caller guarantees it): Cody-Waite by 2*pi, then MUFU.SIN
+__device__ __forceinline__ float sin_below_100pi(float x) {
+  const float q = rint_small(__fmul_rn(x, 0.15915494309189535f));
+  float r = __fmaf_rn(-q, 6.2831854820251465f, x);
+  r = __fmaf_rn(q, 1.7484555e-7f, r);      // 2*pi = 6.2831854820251465 - 1.7484555e-7
+  return __sinf(r);
+}
 __device__ __forceinline__ float safe_sin_fast(float x) {
   const float t = 314.159271240234375f;  // fl32(100*pi)
   if (!(fabsf(x) < t)) {
@@ -97,10 +111,7 @@ __device__ __forceinline__ float safe_sin_fast(float x) {
     else if (r >= t) r = __fsub_rn(r, t);
     x = r;
   }
-  const float q = rintf(__fmul_rn(x, 0.15915494309189535f));
-  float r = __fmaf_rn(-q, 6.2831854820251465f, x);
-  r = __fmaf_rn(q, 1.7484555e-7f, r);      // 2*pi = 6.2831854820251465 - 1.7484555e-7
-  return __sinf(r);
+  return sin_below_100pi(x);
 }
 
 // sin and cos of the same reduced argument (the cosine is d/dx safe_sin(x), used by the tangent
@@ -114,7 +125,7 @@ __device__ __forceinline__ void safe_sincos_fast(float x, float& sn, float& cs) 
     else if (r >= t) r = __fsub_rn(r, t);
     x = r;
   }
-  const float q = rintf(__fmul_rn(x, 0.15915494309189535f));
+  const float q = rint_small(__fmul_rn(x, 0.15915494309189535f));
   float r = __fmaf_rn(-q, 6.2831854820251465f, x);
   r = __fmaf_rn(q, 1.7484555e-7f, r);
   sn = __sinf(r);

@@ -277,7 +277,9 @@ encode_fast_kernel(mnrf_encode_desc d, int G, int nseg, int seg_len, const float
     // phase B: G samples at a time
     for (int s0 = s_begin; s0 < s_end; s0 += G) {
       const int g = min(G, s_end - s0);
-      for (int j = lane; j < g * K; j += 32) {
+      for (int j0 = 0; j0 < g * K; j0 += 32) {
+        // uniform trip count (warp-wide max below): lanes past the last item redo it and store the same values
+        const int j = min(j0 + lane, g * K - 1);
         const int sl = j / K;
         const int k = j - sl * K;
         const float* gp = gs + (s0 + sl) * kGaussStride;
@@ -291,9 +293,27 @@ encode_fast_kernel(mnrf_encode_desc d, int G, int nseg, int seg_len, const float
         float v = lv * (sc0 * sc0);
         __nv_bfloat16* rp = row + sl * row_elems + k;
         float* fp = feat_f32 ? feat_f32 + ((size_t)ray * S + s0 + sl) * (size_t)(2 * KL) + k : nullptr;
+        // Leading degrees for which EVERY lane's |y| and |y + pi/2| stay below 100*pi need none of safe_sin's
+        // large-argument handling (two compare-and-branch pairs with their reconvergence barriers per degree, a
+        // fifth of the loop's instructions): |y| 2^l <= 311  <=>  l <= floor(log2(311 / |y|)), read off the exponent.
+        const float ymax = warp_max(fabsf(y));
+        int n_fast = ((__float_as_int(__fdividef(311.f, ymax)) >> 23) & 0xff) - 126;
+        n_fast = min(max(n_fast, 0), L);
+        int l = 0;
 #pragma unroll 4
-        for (int l = 0; l < L; ++l) {
+        for (; l < n_fast; ++l) {
           // exp(-v/2): (-0.5 v) is exact, so one multiply by -0.5*log2(e) rounds like __expf's own
+          const float e = ex2_ftz(v * -0.72134751081466674805f);
+          const float fs = e * sin_below_100pi(y);
+          const float fc = e * sin_below_100pi(y + 1.57079637050628662109375f);
+          rp[l * K] = __float2bfloat16(fs);
+          rp[KL + l * K] = __float2bfloat16(fc);
+          if (fp) { fp[l * K] = fs; fp[KL + l * K] = fc; }
+          y = y * 2.f;
+          v = v * 4.f;
+        }
+#pragma unroll 2
+        for (; l < L; ++l) {
           const float e = ex2_ftz(v * -0.72134751081466674805f);
           const float fs = e * safe_sin_fast(y);
           const float fc = e * safe_sin_fast(y + 1.57079637050628662109375f);

@@ -325,22 +325,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           wq[jq] = side_w_fetch(kb + kSidePf);
           mbar_wait(&mdone_bar[sstage], sphase, 6);
           if (do_b) {
-            const uint8_t* sbp = smem_b + sstage * B_STAGE + b_off;
+            const uint32_t sbp = smem_u32(smem_b) + sstage * B_STAGE + b_off;
 #pragma unroll 8
             for (int i = 0; i < b_rpg; ++i) {
               const int r = bg * b_rpg + i;
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(sbp + r * 128 + ((b_chunk ^ (r & 7)) << 4));
+              const uint32_t w = ld_shared_u32(sbp + r * 128 + ((b_chunk ^ (r & 7)) << 4));
               bs0 += bf16_lo(w);
               bs1 += bf16_hi(w);
             }
           }
           if (do_a) {
-            const uint8_t* sap = smem_a + sstage * A_STAGE_BYTES + a_off;
+            const uint32_t sap = smem_u32(smem_a) + sstage * A_STAGE_BYTES + a_off;
 #pragma unroll 8
             for (int i = 0; i < 16; ++i) {
               const int r = ag * 16 + i;
               const float wr = __shfl_sync(0xffffffffu, wcur, i);
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(sap + r * 128 + ((a_chunk ^ (r & 7)) << 4));
+              const uint32_t w = ld_shared_u32(sap + r * 128 + ((a_chunk ^ (r & 7)) << 4));
               as0 += wr * bf16_lo(w);
               as1 += wr * bf16_hi(w);
             }
@@ -495,6 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // 64-column groups: two 32-column halves share one 32x128-byte swizzled staging slab
           const int half = ci & 1;
           uint8_t* slab = smem_out + (ew * OUT_STAGES + (store_it % OUT_STAGES)) * (32 * 128);
+          const uint32_t slab_s = smem_u32(slab) + lane * 128;
           if (half == 0) {
             // the bulk store previously issued from this slab must have finished reading it
             if (lane == 0) tma_store_wait_read<OUT_STAGES - 1>();
@@ -503,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int chunk = half * 4 + g;
-            *reinterpret_cast<uint4*>(slab + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o[g];
+            st_shared_v4(slab_s + ((chunk ^ (lane & 7)) << 4), o[g].x, o[g].y, o[g].z, o[g].w);
           }
           if (half == 1) {
             fence_proxy_async();
