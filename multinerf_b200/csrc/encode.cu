@@ -219,7 +219,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 
 // A ray may be split into `nseg` segments of `seg_len` samples (a multiple of G), one warp each: with few rays per
 // launch (a 2048-ray shard of an 8-GPU step) one warp per ray leaves most of the machine idle.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 encode_fast_kernel(mnrf_encode_desc d, int G, int nseg, int seg_len, const float* __restrict__ sdist,
                    const float* __restrict__ origins, const float* __restrict__ directions,
                    const float* __restrict__ radii, const float* __restrict__ near,
@@ -242,6 +242,7 @@ encode_fast_kernel(mnrf_encode_desc d, int G, int nseg, int seg_len, const float
   __syncthreads();
   for (int i = lane; i < G * row_elems; i += 32) row[i] = __float2bfloat16(0.f);   // zero pad columns once
   const float sc0 = __int_as_float((127 + d.min_deg) << 23);       // 2^min_deg
+  const float sc_top = exp2f((float)(L + 1));                      // bound on the growth of |y| over the degrees (+ pi/2)
   const int chunks = row_bytes / 16;
 
   const int64_t num_items = (int64_t)d.num_rays * nseg;
@@ -312,7 +313,21 @@ encode_fast_kernel(mnrf_encode_desc d, int G, int nseg, int seg_len, const float
           y = y * 2.f;
           v = v * 4.f;
         }
-#pragma unroll 2
+        // remaining degrees: the branch-free large-argument form while every argument stays below its 1.3e9 limit
+        // (warp-uniform test), the general one otherwise
+        if (ymax * sc_top < 1e9f) {
+#pragma unroll 4
+          for (; l < L; ++l) {
+            const float e = ex2_ftz(v * -0.72134751081466674805f);
+            const float fs = e * safe_sin_nobranch(y);
+            const float fc = e * safe_sin_nobranch(y + 1.57079637050628662109375f);
+            rp[l * K] = __float2bfloat16(fs);
+            rp[KL + l * K] = __float2bfloat16(fc);
+            if (fp) { fp[l * K] = fs; fp[KL + l * K] = fc; }
+            y = y * 2.f;
+            v = v * 4.f;
+          }
+        }
         for (; l < L; ++l) {
           const float e = ex2_ftz(v * -0.72134751081466674805f);
           const float fs = e * safe_sin_fast(y);
