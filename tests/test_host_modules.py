@@ -241,3 +241,133 @@ def test_llff_loader_with_colmap_model(tmp_path):
   rp = datasets.load_dataset('test', root, configs.Config(dataset_loader='llff', factor=2, batch_size=8, render_path=True,
                                                            render_path_frames=5), device='cpu')
   assert rp.size == 5 and _no_cast(rp).rgb is None
+
+
+def _png(path, arr):
+  from PIL import Image
+  os.makedirs(os.path.dirname(path), exist_ok=True)
+  Image.fromarray(arr).save(path)
+
+
+def test_tanks_and_temples_nerfpp_loader(tmp_path):
+  """NeRF++'s layout (datasets.py:720-764): <split>/{pose,intrinsics,rgb}/*, poses flipped to OpenGL axes,
+  focal from the first intrinsics matrix; render_path reads camera_path/ and only the image size from test/rgb."""
+  from multinerf_b200 import camera_utils, configs, datasets
+  rng = np.random.default_rng(11)
+  root = str(tmp_path)
+  poses, imgs = [], []
+  for split, n in (('train', 3), ('test', 2), ('camera_path', 4)):
+    for i in range(n):
+      m = np.eye(4)
+      m[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+      m[:3, 3] = rng.normal(size=3)
+      K = np.eye(4)
+      K[0, 0] = K[1, 1] = 37.5
+      K[0, 2], K[1, 2] = 5., 3.
+      for d, mat in (('pose', m), ('intrinsics', K)):
+        os.makedirs(os.path.join(root, split, d), exist_ok=True)
+        np.savetxt(os.path.join(root, split, d, f'{i:03d}.txt'), mat.reshape(1, 16))
+      if split != 'camera_path':
+        img = rng.integers(0, 256, (6, 10, 3), dtype=np.uint8)
+        _png(os.path.join(root, split, 'rgb', f'{i:03d}.png'), img)
+      if split == 'train':
+        poses.append(m)
+        imgs.append(img)
+  cfg = configs.Config(dataset_loader='tat_nerfpp', batch_size=8)
+  ds = datasets.load_dataset('train', root, cfg, device='cpu')
+  assert ds.size == 3 and (ds.height, ds.width) == (6, 10) and ds.focal == pytest.approx(37.5)
+  np.testing.assert_allclose(ds.images, np.stack(imgs).astype(np.float32) / 255., atol=1e-7)
+  np.testing.assert_allclose(ds.camtoworlds, np.stack(poses) @ np.diag([1., -1., -1., 1.]), atol=1e-12)
+  np.testing.assert_allclose(ds.pixtocams, camera_utils.get_pixtocam(37.5, 10, 6), atol=1e-12)
+  b = _no_cast(ds)
+  assert b.rays.pix_x_int.shape == (8, 1, 1) and b.rgb.shape == (8, 1, 1, 3)
+  dr = datasets.load_dataset('test', root, configs.Config(dataset_loader='tat_nerfpp', render_path=True), device='cpu')
+  assert dr.size == 4 and dr.images is None and (dr.height, dr.width) == (6, 10)
+
+
+def test_tanks_and_temples_fvs_loader(tmp_path):
+  """Free View Synthesis' layout (datasets.py:767-829): dense/ibr3d_pw_<scale>/{im_*.jpg|png, Ks, Rs, ts}.npy; world-to-camera
+  [R|t] inverted and flipped, PCA-aligned; every llffhold-th view is the test split; `factor` indexes the size list
+  from the largest."""
+  from multinerf_b200 import camera_utils, configs, datasets
+  rng = np.random.default_rng(12)
+  n = 9
+  Rs = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(n)])
+  ts = rng.normal(size=(n, 3))
+  Ks = np.tile(np.array([[50., 0, 4], [0, 50., 3], [0, 0, 1]]), (n, 1, 1))
+  imgs = {}
+  for scale, (H, W) in (('0.25', (3, 4)), ('0.50', (6, 8))):
+    d = os.path.join(str(tmp_path), 'dense', f'ibr3d_pw_{scale}')
+    os.makedirs(d)
+    imgs[scale] = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    for i in range(n):
+      _png(os.path.join(d, f'im_{i:08d}.png'), imgs[scale][i])
+    for name, arr in (('Ks', Ks * (1.0 if scale == '0.50' else 0.5)), ('Rs', Rs), ('ts', ts)):
+      np.save(os.path.join(d, f'{name}.npy'), arr)
+  cfg = configs.Config(dataset_loader='tat_fvs', batch_size=8, factor=0, llffhold=4)
+  ds = datasets.load_dataset('train', str(tmp_path), cfg, device='cpu')
+  keep = np.array([i for i in range(n) if i % 4 != 0])
+  assert ds.size == len(keep) and (ds.height, ds.width) == (6, 8) and ds.focal == pytest.approx(50.)
+  np.testing.assert_allclose(ds.images, imgs['0.50'][keep].astype(np.float32) / 255., atol=1e-7)
+  w2c = np.concatenate([Rs, ts[..., None]], -1)
+  c2w = np.linalg.inv(camera_utils.pad_poses(w2c))[:, :3, :4] @ np.diag([1., -1., -1., 1.])
+  want, _ = camera_utils.transform_poses_pca(c2w)
+  np.testing.assert_allclose(ds.camtoworlds, want[keep], atol=1e-10)
+  dt = datasets.load_dataset('test', str(tmp_path), cfg, device='cpu')
+  assert dt.size == 3
+  np.testing.assert_allclose(dt.camtoworlds, want[[0, 4, 8]], atol=1e-10)
+  d1 = datasets.load_dataset('train', str(tmp_path), configs.Config(dataset_loader='tat_fvs', factor=1, llffhold=4), device='cpu')
+  assert (d1.height, d1.width) == (3, 4) and d1.focal == pytest.approx(25.)
+  with pytest.raises(ValueError):
+    datasets.load_dataset('train', str(tmp_path), configs.Config(dataset_loader='tat_fvs', factor=2), device='cpu')
+  dp = datasets.load_dataset('test', str(tmp_path), configs.Config(dataset_loader='tat_fvs', render_path=True,
+                                                                    render_path_frames=6, llffhold=4), device='cpu')
+  assert dp.images is None and dp.camtoworlds.shape[0] == 6
+
+
+def test_dtu_loader(tmp_path):
+  """DTU (datasets.py:832-911): rect_XXX_<light>.png under <scan>/, projection matrices under ../../cal18/pos_XXX.txt
+  decomposed into intrinsics and pose; poses recentred, scaled into the unit cube, flipped to OpenGL axes."""
+  from multinerf_b200 import camera_utils, configs, datasets
+  rng = np.random.default_rng(13)
+  root = str(tmp_path)
+  scan = os.path.join(root, 'Rectified', 'scan1')
+  cal = os.path.join(root, 'cal18')
+  os.makedirs(scan)
+  os.makedirs(cal)
+  n, H, W = 9, 6, 8
+  K = np.array([[60., 0, 4], [0, 60., 3], [0, 0, 1]])
+  imgs, c2ws = [], []
+  for i in range(1, n + 1):
+    R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    if np.linalg.det(R) < 0:
+      R[:, 0] *= -1
+    C = rng.normal(size=3) * 2
+    P = K @ np.concatenate([R, (-R @ C)[:, None]], -1)          # world -> pixel, camera centre C
+    np.savetxt(os.path.join(cal, f'pos_{i:03d}.txt'), P)
+    for light in range(7):                                        # 7 light conditions + 'max' = 8 files per view
+      img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+      _png(os.path.join(scan, f'rect_{i:03d}_{light}_r5000.png'), img)
+      if light == 3:
+        imgs.append(img)
+    _png(os.path.join(scan, f'rect_{i:03d}_max.png'), rng.integers(0, 256, (H, W, 3), dtype=np.uint8))
+    pose = np.eye(4)
+    pose[:3, :3] = R.T
+    pose[:3, 3] = C
+    c2ws.append(pose[:3])
+  cfg = configs.Config(dataset_loader='dtu', batch_size=8, factor=0)
+  ds = datasets.load_dataset('train', scan, cfg, device='cpu')
+  keep = np.array([i for i in range(n) if i % 8 != 0])
+  assert ds.size == len(keep) and (ds.height, ds.width) == (H, W)
+  np.testing.assert_allclose(ds.images, np.stack(imgs)[keep].astype(np.float32) / 255., atol=1e-7)
+  np.testing.assert_allclose(ds.pixtocams[0], np.linalg.inv(K), atol=1e-4)
+  want, _ = camera_utils.recenter_poses(np.stack(c2ws).astype(np.float32))
+  want = want.copy()
+  want[:, :3, -1] /= np.max(np.abs(want[:, :3, -1]))
+  want = want @ np.diag([1., -1., -1., 1.]).astype(np.float32)
+  np.testing.assert_allclose(ds.camtoworlds, want[keep], atol=2e-4)
+  assert np.abs(ds.camtoworlds[:, :3, 3]).max() <= 1.0 + 1e-5
+  dt = datasets.load_dataset('test', scan, cfg, device='cpu')
+  assert dt.size == 2                                              # views 0 and 8
+  with pytest.raises(ValueError):
+    datasets.load_dataset('train', scan, configs.Config(dataset_loader='dtu', render_path=True), device='cpu')
