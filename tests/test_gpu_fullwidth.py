@@ -143,9 +143,14 @@ def test_fullwidth_train_step_vs_oracle(mods, which):
   state, stats, _ = step_fn(rand, state, utils.Batch(rays=rays, rgb=target), None, 0.5)
   torch.cuda.synchronize()
   stats.materialize()
-  close(stats['mses'], stats_o['mses'].detach(), atol=2e-3, rtol=3e-2, msg=f'{which} mses')
+  # measured on B200 (profiles/r02d_psnr_parity.txt, same cases): per-level mse within 3.1e-5 relative, PSNR within
+  # 1e-4 dB -- train.py's printed PSNRs (3 decimals, train.py:210-214) agree -- and the loss within 2.2e-4 relative;
+  # asserted with an order of magnitude of head-room
+  close(stats['mses'], stats_o['mses'].detach(), atol=1e-6, rtol=2e-3, msg=f'{which} mses')
+  psnr_o = -10.0 / np.log(10.0) * np.log(stats_o['mses'].detach().double().numpy())
+  close(stats['psnrs'], psnr_o, atol=5e-3, rtol=0, msg=f'{which} per-level PSNR (dB)')
   lo = float(stats_o['loss'].detach())
-  assert abs(stats['loss'] - lo) < 3e-2 * max(1.0, abs(lo)), (stats['loss'], lo)
+  assert abs(stats['loss'] - lo) < 3e-3 * max(1.0, abs(lo)), (stats['loss'], lo)
   for k in ('interlevel', 'distortion', 'orientation', 'predicted_normals'):
     if k in stats_o['losses'] and float(stats_o['losses'][k].detach()) != 0.0:
       v = float(stats_o['losses'][k].detach())
