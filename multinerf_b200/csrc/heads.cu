@@ -1,8 +1,9 @@
 // Narrow Dense heads (1-4 outputs), bias-gradient column sums, weight repacking, clip+Adam.
 //
 // Heads replace the Dense(1) density head models.py:460, Dense(3) rgb head :585 and the other
-// <=4-wide heads (:495,515,518,521); they are HBM-bound row reductions (one warp per row,
-// 16-byte loads), not GEMM-shaped work.  Optimizer: train_utils.clip_gradients
+// <=4-wide heads (:495,515,518,521); they are HBM-bound row reductions (16-byte loads; rows of up to 256
+// inputs: K/8 lanes per row and four rows in flight per lane -- head_*_sub_kernel; wider rows: one warp per
+// row), not GEMM-shaped work.  Optimizer: train_utils.clip_gradients
 // train_utils.py:200-218 + nan_to_num :328 + optax.adam (restated, see oracle/o_train.py).
 #include <algorithm>
 
